@@ -1,0 +1,853 @@
+// qoa_api.cu — host side of libqoa_b200.so: the C ABI of include/qoa_b200.h on top of the sm_100a kernels.
+//
+// Mirrors the reference crate's host logic for the hot path (paths into rafaelcaricio/qoaudio):
+//   QoaEncoder::new validation order      src/lib.rs:335-345
+//   QoaEncoder::encode length check       src/lib.rs:368, size formula :374-378
+//   QoaEncoder::encode_frame validation   src/lib.rs:424-430
+//   write_header                          src/lib.rs:404-408
+// There is deliberately no CPU implementation of encode/decode in this file: without a CUDA device every compute
+// entry point fails with QOA_B200_E_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "qoa_kernels.h"
+
+using namespace qoa;
+
+namespace {
+
+std::string g_create_error;
+
+struct PoolBlock {
+    void *ptr;
+    size_t size;
+    bool free;
+};
+
+} // namespace
+
+struct qoa_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    uint64_t launches = 0;
+    std::vector<PoolBlock> pool;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+
+    void *alloc(size_t bytes)
+    {
+        if (bytes == 0) bytes = 16;
+        PoolBlock *best = nullptr;
+        for (auto &b : pool)
+            if (b.free && b.size >= bytes && b.size <= bytes * 2 + 4096 && (!best || b.size < best->size)) best = &b;
+        if (best) {
+            best->free = false;
+            return best->ptr;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            // drop cached free blocks and retry once
+            cudaGetLastError();
+            for (auto &b : pool)
+                if (b.free && b.ptr) {
+                    cudaFree(b.ptr);
+                    b.ptr = nullptr;
+                }
+            pool.erase(std::remove_if(pool.begin(), pool.end(), [](const PoolBlock &b) { return b.ptr == nullptr; }),
+                       pool.end());
+            if (cudaMalloc(&p, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        pool.push_back({p, bytes, false});
+        return p;
+    }
+    void release(void *p)
+    {
+        if (!p) return;
+        for (auto &b : pool)
+            if (b.ptr == p) {
+                b.free = true;
+                return;
+            }
+    }
+    // Scratch blocks are recycled without waiting: safe as long as work is enqueued on one stream at a time.
+    void enter(cudaStream_t s)
+    {
+        if (used && s != last_stream) cudaStreamSynchronize(last_stream);
+        last_stream = s;
+        used = true;
+    }
+};
+
+#define CHECK_CUDA(ctx, expr)                                                                        \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+            cudaGetLastError();                                                                      \
+            return QOA_B200_E_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+// RAII for pooled scratch: blocks go back to the pool when the call returns (the stream still owns their contents
+// until it drains; see qoa_b200_ctx::enter).
+struct Scratch {
+    qoa_b200_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(qoa_b200_ctx *c) : ctx(c) {}
+    ~Scratch()
+    {
+        for (void *p : ptrs) ctx->release(p);
+    }
+    template <typename T>
+    T *get(size_t count)
+    {
+        void *p = ctx->alloc(count * sizeof(T));
+        if (p) ptrs.push_back(p);
+        return static_cast<T *>(p);
+    }
+};
+
+extern "C" {
+
+const char *qoa_b200_version(void) { return "qoa_b200 0.1 (sm_100a)"; }
+
+int qoa_b200_ctx_create(int device, qoa_b200_ctx **out)
+{
+    if (!out) return QOA_B200_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count == 0");
+        cudaGetLastError();
+        return QOA_B200_E_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device index out of range";
+        return QOA_B200_E_ARG;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return QOA_B200_E_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (compute capability " + std::to_string(prop.major) + "." +
+                         std::to_string(prop.minor) + "); this library carries sm_100a code only";
+        return QOA_B200_E_CUDA;
+    }
+    auto *ctx = new qoa_b200_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return 0;
+}
+
+void qoa_b200_ctx_destroy(qoa_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &b : ctx->pool)
+        if (b.ptr) cudaFree(b.ptr);
+    delete ctx;
+}
+
+const char *qoa_b200_last_error(const qoa_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t qoa_b200_kernel_launches(const qoa_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+size_t qoa_b200_encoded_size(uint32_t channels, uint32_t samples) // src/lib.rs:374-378
+{
+    const size_t total = samples, ch = channels;
+    const size_t num_slices = (total + QOA_B200_SLICE_LEN - 1) / QOA_B200_SLICE_LEN;
+    const size_t num_frames = (total + QOA_B200_FRAME_LEN - 1) / QOA_B200_FRAME_LEN;
+    return QOA_B200_HEADER_SIZE + num_frames * (8 + 16 * ch) + num_slices * 8 * ch;
+}
+
+size_t qoa_b200_frame_size(uint32_t channels, uint32_t frame_samples) // src/lib.rs:602-604
+{
+    const size_t slices = ((size_t)frame_samples + QOA_B200_SLICE_LEN - 1) / QOA_B200_SLICE_LEN;
+    return 8 + 16 * (size_t)channels + 8 * slices * channels;
+}
+
+} // extern "C"
+
+// ================================================================================================================
+// encode
+// ================================================================================================================
+
+namespace {
+
+int validate_desc(const qoa_b200_desc &d) // QoaEncoder::new :336-345, in this order
+{
+    if (d.channels == 0 || d.channels > QOA_B200_MAX_CHANNELS) return QOA_B200_ENC_INVALID_CHANNELS;
+    if (d.sample_rate == 0) return QOA_B200_ENC_INVALID_SAMPLE_RATE;
+    if (d.samples == 0) return QOA_B200_ENC_INVALID_SAMPLES;
+    return QOA_B200_OK;
+}
+
+const int32_t kInitLms[8] = {0, 0, 0, 0, 0, 0, -(1 << 13), 1 << 14}; // :348-351
+
+// Uploads jobs + the chain table and launches the encode kernel.  d_lms holds 8 x i32 per chain at job.lms_base + c.
+int run_encode_jobs(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<EncJob> &jobs, const int16_t *d_pcm, uint8_t *d_out,
+                    int32_t *d_lms, cudaStream_t s)
+{
+    std::vector<EncChain> chains;
+    for (uint32_t j = 0; j < jobs.size(); ++j)
+        if (jobs[j].nsamples)
+            for (uint32_t c = 0; c < jobs[j].channels; ++c) chains.push_back({j, c});
+    if (chains.empty()) return 0;
+    EncJob *d_jobs = sc.get<EncJob>(jobs.size());
+    EncChain *d_chains = sc.get<EncChain>(chains.size());
+    if (!d_jobs || !d_chains) {
+        ctx->err = "out of device memory (encode tables)";
+        return QOA_B200_E_NOMEM;
+    }
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(EncJob), cudaMemcpyHostToDevice, s));
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_chains, chains.data(), chains.size() * sizeof(EncChain), cudaMemcpyHostToDevice, s));
+    int nl = 0;
+    CHECK_CUDA(ctx, launch_encode(d_pcm, d_out, d_jobs, d_chains, (uint32_t)chains.size(), d_lms, s, &nl));
+    ctx->launches += nl;
+    return 0;
+}
+
+} // namespace
+
+extern "C" int qoa_b200_encode_all_batch_dev(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *d_pcm,
+                                             const uint64_t *pcm_off, const size_t *pcm_len, uint8_t *d_out,
+                                             const uint64_t *out_off, const size_t *out_cap, size_t *out_len,
+                                             int32_t *status, size_t n, void *stream)
+{
+    if (!ctx) return QOA_B200_E_ARG;
+    if (n == 0) return 0;
+    if (!descs || !d_pcm || !pcm_off || !pcm_len || !d_out || !out_off || !out_cap || !status) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->enter(s);
+    Scratch sc(ctx);
+    std::vector<EncJob> jobs(n);
+    std::vector<int32_t> lms_init;
+    uint32_t chains = 0;
+    for (size_t i = 0; i < n; ++i) {
+        EncJob &j = jobs[i];
+        memset(&j, 0, sizeof j);
+        if (out_len) out_len[i] = 0;
+        int st = validate_desc(descs[i]);
+        if (st == QOA_B200_OK && pcm_len[i] != (size_t)descs[i].samples * descs[i].channels) st = QOA_B200_ENC_INVALID_SAMPLES; // :368
+        const size_t need = st == QOA_B200_OK ? qoa_b200_encoded_size(descs[i].channels, descs[i].samples) : 0;
+        if (st == QOA_B200_OK && out_cap[i] < need) st = QOA_B200_ENC_IO_ERROR;
+        if (st == QOA_B200_OK && (out_off[i] & 7)) {
+            ctx->err = "out_off must be a multiple of 8";
+            return QOA_B200_E_ARG;
+        }
+        status[i] = st;
+        if (st != QOA_B200_OK) continue;
+        j.pcm_off = pcm_off[i];
+        j.out_off = out_off[i];
+        j.channels = descs[i].channels;
+        j.rate = descs[i].sample_rate;
+        j.nsamples = descs[i].samples;
+        j.lms_base = chains;
+        j.file_samples = descs[i].samples;
+        j.flags = 1; // write the 8-byte file header first
+        chains += j.channels;
+        if (out_len) out_len[i] = need;
+    }
+    if (chains == 0) return 0;
+    lms_init.resize((size_t)chains * 8);
+    for (uint32_t c = 0; c < chains; ++c) memcpy(&lms_init[(size_t)c * 8], kInitLms, sizeof kInitLms);
+    int32_t *d_lms = sc.get<int32_t>(lms_init.size());
+    if (!d_lms) {
+        ctx->err = "out of device memory (LMS state)";
+        return QOA_B200_E_NOMEM;
+    }
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_lms, lms_init.data(), lms_init.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    return run_encode_jobs(ctx, sc, jobs, d_pcm, d_out, d_lms, s);
+}
+
+extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
+                                         const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
+                                         size_t *out_len, int32_t *status, size_t n)
+{
+    if (!ctx) return QOA_B200_E_ARG;
+    if (n == 0) return 0;
+    if (!descs || !pcm || !pcm_len || !out || !out_cap || !out_len || !status) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+    // lay the valid streams out in two device arenas
+    std::vector<uint64_t> pcm_off(n, 0), out_off(n, 0);
+    std::vector<size_t> caps(n, 0);
+    uint64_t pcm_total = 0, out_total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        int st = validate_desc(descs[i]);
+        if (st == QOA_B200_OK && pcm_len[i] != (size_t)descs[i].samples * descs[i].channels) st = QOA_B200_ENC_INVALID_SAMPLES;
+        if (st != QOA_B200_OK || !pcm[i] || !out[i]) continue;
+        pcm_off[i] = pcm_total;
+        pcm_total += (pcm_len[i] + 7) & ~(uint64_t)7;
+        out_off[i] = out_total;
+        const size_t need = qoa_b200_encoded_size(descs[i].channels, descs[i].samples);
+        caps[i] = std::min(out_cap[i], need);
+        out_total += (need + 15) & ~(uint64_t)15;
+    }
+    ctx->enter(s);
+    int rc;
+    {
+        Scratch sc(ctx);
+        int16_t *d_pcm = sc.get<int16_t>(pcm_total + 8);
+        uint8_t *d_out = sc.get<uint8_t>(out_total + 16);
+        if (!d_pcm || !d_out) {
+            ctx->err = "out of device memory (encode arenas)";
+            return QOA_B200_E_NOMEM;
+        }
+        for (size_t i = 0; i < n; ++i)
+            if (caps[i])
+                CHECK_CUDA(ctx, cudaMemcpyAsync(d_pcm + pcm_off[i], pcm[i], pcm_len[i] * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        rc = qoa_b200_encode_all_batch_dev(ctx, descs, d_pcm, pcm_off.data(), pcm_len, d_out, out_off.data(), caps.data(),
+                                           out_len, status, n, s);
+        if (rc != 0) return rc;
+        for (size_t i = 0; i < n; ++i)
+            if (status[i] == QOA_B200_OK && out_len[i])
+                CHECK_CUDA(ctx, cudaMemcpyAsync(out[i], d_out + out_off[i], out_len[i], cudaMemcpyDeviceToHost, s));
+        CHECK_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+// ---- streaming encoder ------------------------------------------------------------------------------------------
+
+struct qoa_b200_encoder_batch {
+    qoa_b200_ctx *ctx = nullptr;
+    std::vector<qoa_b200_desc> descs;
+    std::vector<int32_t> new_status;
+    std::vector<uint32_t> lms_base;
+    int32_t *d_lms = nullptr;
+    uint32_t chains = 0;
+};
+
+extern "C" int qoa_b200_encoder_batch_new(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, size_t n, int32_t *status,
+                                          qoa_b200_encoder_batch **out)
+{
+    if (!ctx || !out || (n && !descs)) return QOA_B200_E_ARG;
+    *out = nullptr;
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto *enc = new qoa_b200_encoder_batch();
+    enc->ctx = ctx;
+    enc->descs.assign(descs, descs + n);
+    enc->new_status.resize(n);
+    enc->lms_base.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        enc->new_status[i] = validate_desc(descs[i]);
+        if (status) status[i] = enc->new_status[i];
+        enc->lms_base[i] = enc->chains;
+        if (enc->new_status[i] == QOA_B200_OK) enc->chains += descs[i].channels;
+    }
+    std::vector<int32_t> init((size_t)std::max(enc->chains, 1u) * 8);
+    for (uint32_t c = 0; c < enc->chains; ++c) memcpy(&init[(size_t)c * 8], kInitLms, sizeof kInitLms);
+    cudaError_t e = cudaMalloc(&enc->d_lms, init.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(enc->d_lms, init.data(), init.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("encoder_batch_new: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        if (enc->d_lms) cudaFree(enc->d_lms);
+        delete enc;
+        return QOA_B200_E_CUDA;
+    }
+    *out = enc;
+    return 0;
+}
+
+extern "C" void qoa_b200_encoder_batch_free(qoa_b200_encoder_batch *enc)
+{
+    if (!enc) return;
+    cudaSetDevice(enc->ctx->device);
+    cudaDeviceSynchronize();
+    if (enc->d_lms) cudaFree(enc->d_lms);
+    delete enc;
+}
+
+extern "C" int qoa_b200_encoder_batch_write_header(const qoa_b200_encoder_batch *enc, uint8_t *const *out) // :404-408
+{
+    if (!enc || !out) return QOA_B200_E_ARG;
+    for (size_t i = 0; i < enc->descs.size(); ++i) {
+        if (enc->new_status[i] != QOA_B200_OK || !out[i]) continue;
+        const uint32_t s = enc->descs[i].samples;
+        const uint8_t h[8] = {'q', 'o', 'a', 'f', (uint8_t)(s >> 24), (uint8_t)(s >> 16), (uint8_t)(s >> 8), (uint8_t)s};
+        memcpy(out[i], h, 8);
+    }
+    return 0;
+}
+
+extern "C" int qoa_b200_encoder_batch_encode_chunk_dev(qoa_b200_encoder_batch *enc, const int16_t *d_pcm,
+                                                       const uint64_t *pcm_off, const uint32_t *chunk_samples,
+                                                       uint8_t *d_out, const uint64_t *out_off, void *stream)
+{
+    if (!enc) return QOA_B200_E_ARG;
+    qoa_b200_ctx *ctx = enc->ctx;
+    if (!d_pcm || !pcm_off || !chunk_samples || !d_out || !out_off) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->enter(s);
+    Scratch sc(ctx);
+    const size_t n = enc->descs.size();
+    std::vector<EncJob> jobs(n);
+    for (size_t i = 0; i < n; ++i) {
+        EncJob &j = jobs[i];
+        memset(&j, 0, sizeof j);
+        if (enc->new_status[i] != QOA_B200_OK || chunk_samples[i] == 0) continue;
+        if (out_off[i] & 7) {
+            ctx->err = "out_off must be a multiple of 8";
+            return QOA_B200_E_ARG;
+        }
+        j.pcm_off = pcm_off[i];
+        j.out_off = out_off[i];
+        j.channels = enc->descs[i].channels;
+        j.rate = enc->descs[i].sample_rate;
+        j.nsamples = chunk_samples[i];
+        j.lms_base = enc->lms_base[i];
+    }
+    return run_encode_jobs(ctx, sc, jobs, d_pcm, d_out, enc->d_lms, s);
+}
+
+// Shared body of encode_frame (frame_rules: one frame of <= 5120 samples, :424-430) and encode_chunk (any length).
+static int encode_host(qoa_b200_encoder_batch *enc, const int16_t *const *pcm, const size_t *pcm_len,
+                       uint8_t *const *out, const size_t *out_cap, size_t *written, int32_t *status, bool frame_rules)
+{
+    if (!enc) return QOA_B200_E_ARG;
+    qoa_b200_ctx *ctx = enc->ctx;
+    if (!pcm || !pcm_len || !out || !out_cap || !written || !status) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+    const size_t n = enc->descs.size();
+    std::vector<uint64_t> pcm_off(n, 0), out_off(n, 0);
+    std::vector<uint32_t> chunk(n, 0);
+    std::vector<size_t> fsize(n, 0);
+    uint64_t pcm_total = 0, out_total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        written[i] = 0;
+        if (enc->new_status[i] != QOA_B200_OK) {
+            status[i] = enc->new_status[i];
+            continue;
+        }
+        if (pcm[i] == nullptr && pcm_len[i] == 0) continue; // stream not fed this round
+        const size_t ch = enc->descs[i].channels;
+        // :424-430
+        if (pcm_len[i] == 0 || pcm_len[i] % ch != 0 || (frame_rules && pcm_len[i] / ch > QOA_B200_FRAME_LEN) ||
+            pcm_len[i] / ch > 0xffffffffull) {
+            status[i] = QOA_B200_ENC_INVALID_SAMPLES;
+            continue;
+        }
+        const uint32_t frame_len = (uint32_t)(pcm_len[i] / ch);
+        const size_t fs = qoa_b200_encoded_size((uint32_t)ch, frame_len) - QOA_B200_HEADER_SIZE; // whole frames, no file header
+        if (out_cap[i] < fs || !out[i]) {
+            status[i] = QOA_B200_ENC_IO_ERROR;
+            continue;
+        }
+        status[i] = QOA_B200_OK;
+        chunk[i] = frame_len;
+        fsize[i] = fs;
+        pcm_off[i] = pcm_total;
+        pcm_total += (pcm_len[i] + 7) & ~(uint64_t)7;
+        out_off[i] = out_total;
+        out_total += (fs + 15) & ~(uint64_t)15;
+    }
+    if (pcm_total == 0) return 0;
+    ctx->enter(s);
+    {
+        Scratch sc(ctx);
+        int16_t *d_pcm = sc.get<int16_t>(pcm_total + 8);
+        uint8_t *d_out = sc.get<uint8_t>(out_total + 16);
+        if (!d_pcm || !d_out) {
+            ctx->err = "out of device memory (encode_frame arenas)";
+            return QOA_B200_E_NOMEM;
+        }
+        for (size_t i = 0; i < n; ++i)
+            if (chunk[i])
+                CHECK_CUDA(ctx, cudaMemcpyAsync(d_pcm + pcm_off[i], pcm[i], pcm_len[i] * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        int rc = qoa_b200_encoder_batch_encode_chunk_dev(enc, d_pcm, pcm_off.data(), chunk.data(), d_out, out_off.data(), s);
+        if (rc != 0) return rc;
+        for (size_t i = 0; i < n; ++i)
+            if (chunk[i]) {
+                CHECK_CUDA(ctx, cudaMemcpyAsync(out[i], d_out + out_off[i], fsize[i], cudaMemcpyDeviceToHost, s));
+                written[i] = fsize[i];
+            }
+        CHECK_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+extern "C" int qoa_b200_encoder_batch_encode_frame(qoa_b200_encoder_batch *enc, const int16_t *const *pcm,
+                                                   const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
+                                                   size_t *written, int32_t *status)
+{
+    return encode_host(enc, pcm, pcm_len, out, out_cap, written, status, true);
+}
+
+extern "C" int qoa_b200_encoder_batch_encode_chunk(qoa_b200_encoder_batch *enc, const int16_t *const *pcm,
+                                                   const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
+                                                   size_t *written, int32_t *status)
+{
+    return encode_host(enc, pcm, pcm_len, out, out_cap, written, status, false);
+}
+
+extern "C" int qoa_b200_encoder_batch_get_lms(qoa_b200_encoder_batch *enc, size_t i, uint32_t c, int32_t history[4],
+                                              int32_t weights[4])
+{
+    if (!enc || i >= enc->descs.size() || enc->new_status[i] != QOA_B200_OK || c >= enc->descs[i].channels)
+        return QOA_B200_E_ARG;
+    qoa_b200_ctx *ctx = enc->ctx;
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CHECK_CUDA(ctx, cudaDeviceSynchronize());
+    int32_t st[8];
+    CHECK_CUDA(ctx, cudaMemcpy(st, enc->d_lms + (size_t)(enc->lms_base[i] + c) * 8, sizeof st, cudaMemcpyDeviceToHost));
+    memcpy(history, st, 16);
+    memcpy(weights, st + 4, 16);
+    return 0;
+}
+
+// ================================================================================================================
+// decode
+// ================================================================================================================
+
+struct qoa_b200_decode_plan {
+    qoa_b200_ctx *ctx = nullptr;
+    size_t n = 0;
+    int mode = 0;
+    const uint8_t *d_arena = nullptr; // input bytes (borrowed for *_dev plans, owned otherwise)
+    uint8_t *owned_arena = nullptr;
+    FrameRec *d_recs = nullptr;
+    uint64_t n_frames = 0;
+    uint32_t max_ch = 0;
+    bool all_stereo = false;
+    std::vector<qoa_b200_stream_info> info;
+    std::vector<uint64_t> frame_base; // n + 1
+};
+
+namespace {
+
+int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in_off, const size_t *len, cudaStream_t s)
+{
+    const size_t n = plan->n;
+    Scratch sc(ctx);
+    uint64_t *d_off = sc.get<uint64_t>(n);
+    uint64_t *d_len = sc.get<uint64_t>(n);
+    uint64_t *d_fbase = sc.get<uint64_t>(n + 1);
+    qoa_b200_stream_info *d_info = sc.get<qoa_b200_stream_info>(n);
+    if (!d_off || !d_len || !d_fbase || !d_info) {
+        ctx->err = "out of device memory (index tables)";
+        return QOA_B200_E_NOMEM;
+    }
+    std::vector<uint64_t> len64(len, len + n);
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_len, len64.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CHECK_CUDA(ctx, launch_index_count(plan->d_arena, d_off, d_len, n, plan->mode, d_info, s));
+    ctx->launches += 1;
+    plan->info.resize(n);
+    CHECK_CUDA(ctx, cudaMemcpyAsync(plan->info.data(), d_info, n * sizeof(qoa_b200_stream_info), cudaMemcpyDeviceToHost, s));
+    CHECK_CUDA(ctx, cudaStreamSynchronize(s));
+    plan->frame_base.assign(n + 1, 0);
+    uint32_t max_ch = 0;
+    bool stereo = true;
+    for (size_t i = 0; i < n; ++i) {
+        const auto &inf = plan->info[i];
+        plan->frame_base[i + 1] = plan->frame_base[i] + inf.index_frames;
+        if (inf.index_frames) {
+            max_ch = std::max(max_ch, inf.max_channels);
+            if (inf.max_channels != 2 || !(inf.flags & QOA_B200_INFO_UNIFORM_CH) || !(inf.flags & QOA_B200_INFO_ALIGNED16))
+                stereo = false;
+        }
+    }
+    plan->n_frames = plan->frame_base[n];
+    plan->max_ch = max_ch;
+    plan->all_stereo = stereo && plan->n_frames > 0;
+    if (plan->n_frames) {
+        plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
+        if (!plan->d_recs) {
+            ctx->err = "out of device memory (frame index)";
+            return QOA_B200_E_NOMEM;
+        }
+        CHECK_CUDA(ctx, cudaMemcpyAsync(d_fbase, plan->frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        CHECK_CUDA(ctx, launch_index_fill(plan->d_arena, d_off, d_len, n, plan->mode, d_fbase, plan->d_recs, s));
+        ctx->launches += 1;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" int qoa_b200_decode_plan_create_dev(qoa_b200_ctx *ctx, const uint8_t *d_qoa, const uint64_t *in_off,
+                                               const size_t *len, size_t n, int mode, void *stream,
+                                               qoa_b200_decode_plan **out)
+{
+    if (!ctx || !out) return QOA_B200_E_ARG;
+    *out = nullptr;
+    if (n && (!d_qoa || !in_off || !len)) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    if (mode < QOA_B200_DECODE_ITER || mode > QOA_B200_DECODE_FRAMES) {
+        ctx->err = "bad decode mode";
+        return QOA_B200_E_ARG;
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (in_off[i] & 15) {
+            ctx->err = "in_off must be a multiple of 16";
+            return QOA_B200_E_ARG;
+        }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->enter(s);
+    auto *plan = new qoa_b200_decode_plan();
+    plan->ctx = ctx;
+    plan->n = n;
+    plan->mode = mode;
+    plan->d_arena = d_qoa;
+    if (n) {
+        int rc = plan_index(ctx, plan, in_off, len, s);
+        if (rc != 0) {
+            qoa_b200_decode_plan_destroy(plan);
+            return rc;
+        }
+    }
+    *out = plan;
+    return 0;
+}
+
+extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
+                                           int mode, qoa_b200_decode_plan **out)
+{
+    if (!ctx || !out) return QOA_B200_E_ARG;
+    *out = nullptr;
+    if (n && (!qoa || !len)) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+    ctx->enter(s);
+    std::vector<uint64_t> off(n, 0);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        off[i] = total;
+        total += (len[i] + 15) & ~(uint64_t)15;
+    }
+    uint8_t *arena = static_cast<uint8_t *>(ctx->alloc(total + 16));
+    if (!arena) {
+        ctx->err = "out of device memory (input arena)";
+        return QOA_B200_E_NOMEM;
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (len[i]) {
+            cudaError_t e = cudaMemcpyAsync(arena + off[i], qoa[i], len[i], cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("H2D input copy: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                ctx->release(arena);
+                return QOA_B200_E_CUDA;
+            }
+        }
+    int rc = qoa_b200_decode_plan_create_dev(ctx, arena, off.data(), len, n, mode, s, out);
+    if (rc != 0) {
+        ctx->release(arena);
+        return rc;
+    }
+    (*out)->owned_arena = arena;
+    return 0;
+}
+
+extern "C" void qoa_b200_decode_plan_destroy(qoa_b200_decode_plan *plan)
+{
+    if (!plan) return;
+    plan->ctx->release(plan->d_recs);
+    plan->ctx->release(plan->owned_arena);
+    delete plan;
+}
+
+extern "C" int qoa_b200_decode_plan_info(const qoa_b200_decode_plan *plan, qoa_b200_stream_info *info)
+{
+    if (!plan || (plan->n && !info)) return QOA_B200_E_ARG;
+    if (plan->n) memcpy(info, plan->info.data(), plan->n * sizeof(qoa_b200_stream_info));
+    return 0;
+}
+
+extern "C" size_t qoa_b200_decode_plan_frame_headers(const qoa_b200_decode_plan *plan, size_t i,
+                                                     qoa_b200_frame_header *hdrs, size_t cap)
+{
+    if (!plan || i >= plan->n) return 0;
+    const uint64_t f0 = plan->frame_base[i], f1 = plan->frame_base[i + 1];
+    const size_t count = (size_t)(f1 - f0);
+    const size_t m = std::min(count, cap);
+    if (m && hdrs) {
+        std::vector<FrameRec> recs(m);
+        cudaSetDevice(plan->ctx->device);
+        if (cudaStreamSynchronize(plan->ctx->last_stream) != cudaSuccess ||
+            cudaMemcpy(recs.data(), plan->d_recs + f0, m * sizeof(FrameRec), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        for (size_t k = 0; k < m; ++k) {
+            hdrs[k].num_channels = recs[k].ch;
+            hdrs[k].sample_rate = recs[k].rate;
+            hdrs[k].num_samples_per_channel = recs[k].nspc;
+        }
+    }
+    return count;
+}
+
+extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t *d_out, const uint64_t *out_off,
+                                            const size_t *out_cap, int32_t *status, void *stream)
+{
+    if (!plan) return QOA_B200_E_ARG;
+    qoa_b200_ctx *ctx = plan->ctx;
+    const size_t n = plan->n;
+    if (n == 0) return 0;
+    if (!d_out || !out_off || !out_cap) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->enter(s);
+    Scratch sc(ctx);
+    std::vector<uint64_t> base(n);
+    bool aligned = true;
+    for (size_t i = 0; i < n; ++i) {
+        int st = plan->info[i].status;
+        if (plan->info[i].samples > out_cap[i]) {
+            st = QOA_B200_DEC_OUTPUT_TOO_SMALL;
+            base[i] = ~0ull;
+        } else {
+            base[i] = out_off[i];
+            if (out_off[i] & 7) aligned = false;
+        }
+        if (status) status[i] = st;
+    }
+    if (plan->n_frames == 0) return 0;
+    uint64_t *d_base = sc.get<uint64_t>(n);
+    if (!d_base) {
+        ctx->err = "out of device memory (output table)";
+        return QOA_B200_E_NOMEM;
+    }
+    CHECK_CUDA(ctx, cudaMemcpyAsync(d_base, base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    int nl = 0;
+    CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs, plan->n_frames, plan->max_ch, plan->all_stereo && aligned,
+                                  d_base, d_out, s, &nl));
+    ctx->launches += nl;
+    return 0;
+}
+
+extern "C" int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *const *out, const size_t *out_cap,
+                                        int32_t *status)
+{
+    if (!plan) return QOA_B200_E_ARG;
+    qoa_b200_ctx *ctx = plan->ctx;
+    const size_t n = plan->n;
+    if (n == 0) return 0;
+    if (!out || !out_cap) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->last_stream;
+    std::vector<uint64_t> off(n, 0);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        off[i] = total;
+        if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + 7) & ~(uint64_t)7;
+    }
+    int16_t *d_out = static_cast<int16_t *>(ctx->alloc((total + 8) * sizeof(int16_t)));
+    if (!d_out) {
+        ctx->err = "out of device memory (output arena)";
+        return QOA_B200_E_NOMEM;
+    }
+    int rc = qoa_b200_decode_plan_run_dev(plan, d_out, off.data(), out_cap, status, s);
+    if (rc == 0) {
+        for (size_t i = 0; i < n && rc == 0; ++i) {
+            const uint64_t cnt = plan->info[i].samples;
+            if (cnt == 0 || cnt > out_cap[i] || !out[i]) continue;
+            cudaError_t e = cudaMemcpyAsync(out[i], d_out + off[i], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) {
+                ctx->err = std::string("D2H output copy: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                rc = QOA_B200_E_CUDA;
+            }
+        }
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess && rc == 0) {
+            ctx->err = std::string("decode: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            rc = QOA_B200_E_CUDA;
+        }
+    }
+    ctx->release(d_out);
+    return rc;
+}
+
+extern "C" int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
+                                         int mode, int16_t *const *out, const size_t *out_cap,
+                                         qoa_b200_stream_info *info, int32_t *status)
+{
+    qoa_b200_decode_plan *plan = nullptr;
+    int rc = qoa_b200_decode_plan_create(ctx, qoa, len, n, mode, &plan);
+    if (rc != 0) return rc;
+    if (info) qoa_b200_decode_plan_info(plan, info);
+    rc = qoa_b200_decode_plan_run(plan, out, out_cap, status);
+    qoa_b200_decode_plan_destroy(plan);
+    return rc;
+}
+
+// ================================================================================================================
+// generators / microbenchmarks
+// ================================================================================================================
+
+extern "C" int qoa_b200_gen_pcm_dev(qoa_b200_ctx *ctx, int16_t *d_pcm, uint64_t n_streams, uint64_t first_stream,
+                                    uint32_t channels, uint64_t samples, uint64_t start, uint64_t seed, int kind,
+                                    void *stream)
+{
+    if (!ctx || !d_pcm) return QOA_B200_E_ARG;
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CHECK_CUDA(ctx, launch_gen_pcm(d_pcm, n_streams, first_stream, channels, samples, start, seed, kind,
+                                   static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+extern "C" int qoa_b200_gen_qoa_dev(qoa_b200_ctx *ctx, uint8_t *d_qoa, uint64_t stride, uint64_t n_streams,
+                                    uint64_t first_stream, uint32_t channels, uint32_t sample_rate, uint32_t samples,
+                                    uint64_t seed, void *stream)
+{
+    if (!ctx || !d_qoa || channels == 0 || channels > 255 || (stride & 15) ||
+        stride < qoa_b200_encoded_size(channels, samples))
+        return QOA_B200_E_ARG;
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CHECK_CUDA(ctx, launch_gen_qoa(d_qoa, stride, n_streams, first_stream, channels, sample_rate, samples, seed,
+                                   static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+extern "C" int qoa_b200_int_issue_peak(qoa_b200_ctx *ctx, int kind, double *thread_ops_per_s)
+{
+    if (!ctx || !thread_ops_per_s) return QOA_B200_E_ARG;
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    CHECK_CUDA(ctx, run_int_issue_peak(kind, ctx->sm_count, thread_ops_per_s));
+    return 0;
+}

@@ -1,0 +1,443 @@
+// qoa_decode.cu — frame index pre-pass and frame-parallel decode kernels (sm_100a).
+//
+// Reference semantics (rafaelcaricio/qoaudio, src/lib.rs):
+//   QoaDecoder::new                       :127-169   file header, mode, first frame header
+//   decode_frame_header_and_lms           :205-289   header parse + validation + LMS load, EOF rules
+//   decode_one_slice_per_channel          :291-330   the 20-sample LMS loop
+//   Iterator::next                        :661-693   item order, streaming-mode dummy header
+//   decode_all                            :713-747   extra IncompatibleFrame check
+// Every frame header carries its own LMS state (:270-281), so frames decode independently: one thread owns one
+// (frame, channel pair) and walks its slices; nothing crosses a frame.
+#include "qoa_kernels.h"
+
+namespace qoa {
+
+// ================================================================================================================
+// Index pre-pass
+// ================================================================================================================
+
+__device__ __forceinline__ uint32_t ld_be32(const uint8_t *p) // 4-byte aligned
+{
+    return bswap32(__ldg(reinterpret_cast<const uint32_t *>(p)));
+}
+
+// Walks one stream exactly like QoaDecoder::new + Iterator::next would, without decoding samples.
+template <bool FILL>
+__device__ void walk_stream(const uint8_t *__restrict__ arena, uint64_t off, uint64_t len, int mode, uint32_t stream,
+                            FrameRec *__restrict__ recs, qoa_b200_stream_info *__restrict__ out)
+{
+    const uint8_t *p = arena + off;
+    qoa_b200_stream_info info;
+    info.status = QOA_B200_OK;
+    info.streaming = 0;
+    info.header_samples = 0;
+    info.channels = 0;
+    info.sample_rate = 0;
+    info.index_frames = 0;
+    info.max_channels = 0;
+    info.flags = 0;
+    info.samples = 0;
+    info.frames = 0;
+
+    uint64_t pos = 0;
+    bool streaming = true;
+    bool ok = true;
+    if (mode != QOA_B200_DECODE_FRAMES) { // QoaDecoder::new :128-144
+        if (len < 4) {
+            info.status = QOA_B200_DEC_IO_ERROR;
+            ok = false;
+        } else if (ld_be32(p) != kMagic) {
+            info.status = QOA_B200_DEC_NOT_QOA_FILE;
+            ok = false;
+        } else if (len < 8) {
+            info.status = QOA_B200_DEC_IO_ERROR;
+            ok = false;
+        } else {
+            info.header_samples = ld_be32(p + 4);
+            streaming = info.header_samples == 0;
+            pos = 8;
+        }
+    }
+    info.streaming = (ok && streaming) ? 1 : 0;
+
+    uint64_t items = 0, table_frames = 0, samples = 0;
+    uint32_t first_ch = 0, first_rate = 0, fixed_ch = 0, fixed_rate = 0, max_ch = 0, min_ch = 0xffffffffu;
+    bool aligned = true;
+    bool have_first = false, first = true;
+    if (ok && streaming && mode != QOA_B200_DECODE_FRAMES) { // :674-677 default header replayed first
+        items = 1;
+        have_first = true;
+    }
+    while (ok) {
+        if (len - pos < 8) { // :206-216 EOF at a header is a clean end ...
+            if (!streaming && first) info.status = QOA_B200_DEC_NO_SAMPLES; // ... except in new() :163-165
+            break;
+        }
+        const uint64_t frame_pos = pos;
+        const uint2 hw = ldg_be64(p + pos);
+        pos += 8;
+        const uint32_t ch = hw.x >> 24;            // :217
+        const uint32_t rate = hw.x & 0xffffffu;     // :218
+        const uint32_t nspc = hw.y >> 16;           // :219
+        const uint32_t frame_size = hw.y & 0xffffu; // :220
+        if (ch == 0 || rate == 0) { // :227
+            info.status = QOA_B200_DEC_INVALID_FRAME_HEADER;
+            break;
+        }
+        const uint32_t non_sample = 8 + 16 * ch; // :232
+        if (frame_size <= non_sample) {           // :233
+            info.status = QOA_B200_DEC_INVALID_FRAME_HEADER;
+            break;
+        }
+        const uint32_t num_slices = (frame_size - non_sample) / 8;     // :236-237
+        if (num_slices % ch != 0 || num_slices / ch > kSlicesPerFrame) { // :239, :242
+            info.status = QOA_B200_DEC_INVALID_FRAME_HEADER;
+            break;
+        }
+        if (!streaming) { // :246-259
+            if (first) {
+                fixed_ch = ch;
+                fixed_rate = rate;
+            } else if (ch != fixed_ch || rate != fixed_rate) {
+                info.status = QOA_B200_DEC_INCOMPATIBLE_FRAME;
+                break;
+            }
+        }
+        if (len - pos < 16ull * ch) { // :271-281 read_exact of the LMS block fails
+            info.status = QOA_B200_DEC_IO_ERROR;
+            break;
+        }
+        pos += 16ull * ch;
+        // the FrameHeader item is yielded now (:674-678 / :685)
+        if (mode != QOA_B200_DECODE_FRAMES) items++;
+        if (!have_first) {
+            have_first = true;
+            first_ch = ch;
+            first_rate = rate;
+        } else if (mode == QOA_B200_DECODE_ALL && (ch != first_ch || rate != first_rate)) { // decode_all :735-738
+            info.status = QOA_B200_DEC_INCOMPATIBLE_FRAME;
+            break;
+        }
+        if (mode == QOA_B200_DECODE_FRAMES) items++;
+        // slices: the decoder is driven by nspc, not by frame_size (:679-688, :320-328)
+        const uint64_t groups_needed = (nspc + kSliceLen - 1) / kSliceLen;
+        const uint64_t group_bytes = 8ull * ch;
+        const uint64_t groups_avail = (len - pos) / group_bytes;
+        uint32_t nsamp = nspc;
+        bool truncated = false;
+        if (groups_avail < groups_needed) { // read_exact fails inside a slice group (:301): whole groups before it were yielded
+            nsamp = (uint32_t)groups_avail * kSliceLen;
+            truncated = true;
+        }
+        if (FILL) {
+            FrameRec r;
+            r.in_off = off + frame_pos;
+            r.out_rel = samples;
+            r.stream = stream;
+            r.rate = rate;
+            r.nsamp = (uint16_t)nsamp;
+            r.nspc = (uint16_t)nspc;
+            r.ch = (uint8_t)ch;
+            r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            recs[table_frames] = r;
+        }
+        table_frames++;
+        max_ch = max(max_ch, ch);
+        min_ch = min(min_ch, ch);
+        aligned = aligned && ((samples & 7) == 0);
+        samples += (uint64_t)nsamp * ch;
+        if (truncated) {
+            info.status = QOA_B200_DEC_IO_ERROR;
+            break;
+        }
+        pos += groups_needed * group_bytes;
+        first = false;
+    }
+    if (!FILL) {
+        info.channels = first_ch;
+        info.sample_rate = first_rate;
+        info.samples = samples;
+        info.frames = items;
+        info.index_frames = (uint32_t)table_frames;
+        info.max_channels = max_ch;
+        info.flags = ((table_frames == 0 || max_ch == min_ch) ? QOA_B200_INFO_UNIFORM_CH : 0u) |
+                     (aligned ? QOA_B200_INFO_ALIGNED16 : 0u);
+        *out = info;
+    }
+}
+
+__global__ void index_count_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ in_off,
+                                   const uint64_t *__restrict__ in_len, uint32_t n, int mode,
+                                   qoa_b200_stream_info *__restrict__ info)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    walk_stream<false>(arena, in_off[i], in_len[i], mode, i, nullptr, info + i);
+}
+
+__global__ void index_fill_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ in_off,
+                                  const uint64_t *__restrict__ in_len, uint32_t n, int mode,
+                                  const uint64_t *__restrict__ frame_base, FrameRec *__restrict__ recs)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    walk_stream<true>(arena, in_off[i], in_len[i], mode, i, recs + frame_base[i], nullptr);
+}
+
+cudaError_t launch_index_count(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
+                               int mode, qoa_b200_stream_info *d_info, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const int block = 32; // one dependent-load chain per thread: spread the streams over as many SMs as possible
+    index_count_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(d_arena, d_in_off, d_in_len, (uint32_t)n,
+                                                                             mode, d_info);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_index_fill(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
+                              int mode, const uint64_t *d_frame_base, FrameRec *d_recs, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const int block = 32;
+    index_fill_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(d_arena, d_in_off, d_in_len, (uint32_t)n,
+                                                                            mode, d_frame_base, d_recs);
+    return cudaGetLastError();
+}
+
+// ================================================================================================================
+// Decode
+// ================================================================================================================
+
+constexpr int kDecThreads = 128;
+
+// Dequant LUT in shared memory, replicated per lane so that every lane reads its own bank:
+// entry (sf*8 + code) of lane L lives at byte ((sf*8 + code) * 32 + L) * 4  (16 KiB, conflict-free).
+struct __align__(16384) DecLut {
+    int v[128 * 32];
+};
+
+__device__ __forceinline__ void fill_lut(DecLut &lut)
+{
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) lut.v[i] = c_dequant[i >> 5];
+    __syncthreads();
+}
+
+// LMS state of one channel inside a thread.  s[i] = +1 / -1 is the sign the reference's update() derives from
+// history[i] (src/lib.rs:823-826: history < 0 ? -delta : delta, zero counts as positive).
+struct Chain {
+    int h0, h1, h2, h3;
+    int w0, w1, w2, w3;
+    int s0, s1, s2, s3;
+};
+
+__device__ __forceinline__ int sign_pm1(int v) { return (v >> 31) | 1; }
+
+// 16 bytes: 4 x BE i16 history, 4 x BE i16 weights, sign-extended (:271-281)
+__device__ __forceinline__ void load_lms(Chain &c, const uint8_t *p)
+{
+    const uint2 h = ldg_be64(p);
+    const uint2 w = ldg_be64(p + 8);
+    c.h0 = (int)h.x >> 16;
+    c.h1 = (int)(h.x << 16) >> 16;
+    c.h2 = (int)h.y >> 16;
+    c.h3 = (int)(h.y << 16) >> 16;
+    c.w0 = (int)w.x >> 16;
+    c.w1 = (int)(w.x << 16) >> 16;
+    c.w2 = (int)w.y >> 16;
+    c.w3 = (int)(w.y << 16) >> 16;
+    c.s0 = sign_pm1(c.h0);
+    c.s1 = sign_pm1(c.h1);
+    c.s2 = sign_pm1(c.h2);
+    c.s3 = sign_pm1(c.h3);
+}
+
+// Byte offset (code * 128) of sample I's 3-bit code inside the lane-replicated LUT row.
+// Slice word layout (:303, :308): sf in bits 63..60, sample i's code in bits 59-3i .. 57-3i.
+template <int I>
+__device__ __forceinline__ uint32_t code_off(uint32_t hi, uint32_t lo)
+{
+    constexpr int pos = 57 - 3 * I; // LSB of the code within the 64-bit word
+    constexpr int sh = pos - 7;     // shift that brings the code to bits 9..7
+    uint32_t v;
+    if constexpr (sh >= 32)
+        v = hi >> (sh - 32);
+    else if constexpr (sh > 0)
+        v = __funnelshift_r(lo, hi, sh);
+    else if constexpr (sh == 0)
+        v = lo;
+    else
+        v = lo << (-sh);
+    return v & 0x380u;
+}
+
+__device__ __forceinline__ int lds_s32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// One sample of one channel (:306-317).  `row` = shared address of the lane's LUT row for this slice's scalefactor
+// (1 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
+template <int I>
+__device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
+{
+    const int dq = lds_s32(row | code_off<I>(hi, lo));
+    const int p = (c.w0 * c.h0 + c.w1 * c.h1 + c.w2 * c.h2 + c.w3 * c.h3) >> 13; // predict :799-805
+    const int r = clamp_i16(p + dq);                                              // :310
+    const int d = dq >> 4;                                                        // update :822
+    c.w0 += c.s0 * d;
+    c.w1 += c.s1 * d;
+    c.w2 += c.s2 * d;
+    c.w3 += c.s3 * d;
+    c.h0 = c.h1;
+    c.h1 = c.h2;
+    c.h2 = c.h3;
+    c.h3 = r;
+    c.s0 = c.s1;
+    c.s1 = c.s2;
+    c.s2 = c.s3;
+    c.s3 = sign_pm1(r);
+    return r;
+}
+
+template <int I>
+struct PairLoop {
+    // Decodes samples I..19 of a slice for two channels; o[i] = (r_b << 16) | (r_a & 0xffff).
+    static __device__ __forceinline__ void run(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb,
+                                               uint32_t *o)
+    {
+        const int ra = decode_step<I>(a, row_a, wa.x, wa.y);
+        const int rb = decode_step<I>(b, row_b, wb.x, wb.y);
+        o[I] = __byte_perm((uint32_t)ra, (uint32_t)rb, 0x5410);
+        PairLoop<I + 1>::run(a, b, row_a, row_b, wa, wb, o);
+    }
+};
+template <>
+struct PairLoop<20> {
+    static __device__ __forceinline__ void run(Chain &, Chain &, uint32_t, uint32_t, uint2, uint2, uint32_t *) {}
+};
+
+template <int I>
+struct SingleLoop {
+    static __device__ __forceinline__ void run(Chain &a, uint32_t row_a, uint2 wa, int16_t *o)
+    {
+        o[I] = (int16_t)decode_step<I>(a, row_a, wa.x, wa.y);
+        SingleLoop<I + 1>::run(a, row_a, wa, o);
+    }
+};
+template <>
+struct SingleLoop<20> {
+    static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, int16_t *) {}
+};
+
+// ---- stereo fast path: one thread = one frame (both channels, two independent LMS chains = ILP 2) -------------
+// Requirements (checked by the host from the index flags): every frame has 2 channels and starts 16-byte aligned
+// in the PCM output.
+__global__ void __launch_bounds__(kDecThreads)
+decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
+                     const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
+{
+    __shared__ DecLut lut;
+    fill_lut(lut);
+    const uint64_t fi = (uint64_t)blockIdx.x * kDecThreads + threadIdx.x;
+    if (fi >= n_frames) return;
+    const FrameRec rec = recs[fi];
+    const uint64_t ob = out_base[rec.stream];
+    const uint32_t nsamp = rec.nsamp;
+    if (nsamp == 0 || ob == ~0ull) return;
+
+    const uint8_t *fp = arena + rec.in_off;
+    Chain a, b;
+    load_lms(a, fp + 8);
+    load_lms(b, fp + 24);
+    const uint8_t *sp = fp + 40;
+    const uint32_t nfull = nsamp / kSliceLen;
+    uint32_t *op = reinterpret_cast<uint32_t *>(out + ob + rec.out_rel);
+    const uint32_t lane_row = smem_u32(&lut.v[0]) + (threadIdx.x & 31) * 4;
+
+    for (uint32_t k = 0; k < nfull; ++k) {
+        const uint2 wa = ldg_be64(sp + (uint64_t)k * 16);
+        const uint2 wb = ldg_be64(sp + (uint64_t)k * 16 + 8);
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+        const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+        uint32_t o[20];
+        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+        uint4 *dst = reinterpret_cast<uint4 *>(op + (uint64_t)k * kSliceLen);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    const uint32_t rem = nsamp - nfull * kSliceLen; // partial last slice: decoded in full, `rem` samples emitted (:320-325)
+    if (rem) {
+        const uint2 wa = ldg_be64(sp + (uint64_t)nfull * 16);
+        const uint2 wb = ldg_be64(sp + (uint64_t)nfull * 16 + 8);
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+        const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+        uint32_t o[20];
+        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+        uint32_t *dst = op + (uint64_t)nfull * kSliceLen;
+#pragma unroll
+        for (int i = 0; i < 20; ++i)
+            if ((uint32_t)i < rem) dst[i] = o[i];
+    }
+}
+
+// ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
+__global__ void __launch_bounds__(kDecThreads)
+decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_units,
+                      uint32_t max_ch, const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
+{
+    __shared__ DecLut lut;
+    fill_lut(lut);
+    const uint64_t u = (uint64_t)blockIdx.x * kDecThreads + threadIdx.x;
+    if (u >= n_units) return;
+    const uint64_t fi = u / max_ch;
+    const uint32_t c = (uint32_t)(u - fi * max_ch);
+    const FrameRec rec = recs[fi];
+    const uint32_t ch = rec.ch;
+    const uint32_t nsamp = rec.nsamp;
+    if (c >= ch || nsamp == 0) return;
+    const uint64_t ob = out_base[rec.stream];
+    if (ob == ~0ull) return;
+
+    const uint8_t *fp = arena + rec.in_off;
+    Chain a;
+    load_lms(a, fp + 8 + 16 * c);
+    const uint8_t *sp = fp + 8 + 16 * ch + 8 * c;
+    const uint32_t ngroups = (nsamp + kSliceLen - 1) / kSliceLen;
+    int16_t *op = out + ob + rec.out_rel + c;
+    const uint32_t lane_row = smem_u32(&lut.v[0]) + (threadIdx.x & 31) * 4;
+
+    for (uint32_t k = 0; k < ngroups; ++k) {
+        const uint2 wa = ldg_be64(sp + (uint64_t)k * ch * 8);
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+        int16_t o[20];
+        SingleLoop<0>::run(a, row_a, wa, o);
+        const uint32_t base = k * kSliceLen;
+        const uint32_t emit = min((uint32_t)kSliceLen, nsamp - base); // :320-328
+#pragma unroll
+        for (int i = 0; i < 20; ++i)
+            if ((uint32_t)i < emit) op[(uint64_t)(base + i) * ch] = o[i];
+    }
+}
+
+cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
+                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s, int *n_launches)
+{
+    if (n_frames == 0 || max_ch == 0) return cudaSuccess;
+    if (all_stereo) {
+        const uint64_t blocks = (n_frames + kDecThreads - 1) / kDecThreads;
+        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+        decode_stereo_kernel<<<(unsigned)blocks, kDecThreads, 0, s>>>(d_arena, d_recs, n_frames, d_out_base, d_out);
+    } else {
+        const uint64_t n_units = n_frames * max_ch;
+        const uint64_t blocks = (n_units + kDecThreads - 1) / kDecThreads;
+        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+        decode_generic_kernel<<<(unsigned)blocks, kDecThreads, 0, s>>>(d_arena, d_recs, n_units, max_ch, d_out_base,
+                                                                       d_out);
+    }
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
+} // namespace qoa

@@ -1,0 +1,165 @@
+// qoa_gen.cu — on-device synthetic workload generators and the integer-issue microbenchmark (sm_100a).
+//
+// The PCM recipe is integer-only and counter-based so that tests/signals.py (numpy) and this kernel produce
+// bit-identical data; it is measurement plumbing, not part of the reference's path.
+#include "qoa_kernels.h"
+
+namespace qoa {
+
+__device__ __forceinline__ int tri16(uint32_t phase)
+{
+    const uint32_t ph = phase & 0xffffu;
+    const int t = (int)(ph < 32768u ? ph : 65535u - ph); // 0..32767
+    return t * 2 - 32767;
+}
+
+__global__ void gen_pcm_kernel(int16_t *__restrict__ pcm, uint64_t n_streams, uint64_t first_stream, uint32_t channels,
+                               uint64_t samples, uint64_t start, uint64_t seed, int kind)
+{
+    const uint64_t per_stream = samples * channels;
+    const uint64_t total = n_streams * per_stream;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = e / per_stream;
+        const uint64_t r = e - s * per_stream;
+        const uint64_t i = r / channels + start;
+        const uint32_t c = (uint32_t)(r % channels);
+        const uint64_t k = stream_key(seed, first_stream + s, c);
+        const uint64_t h = splitmix64(k + i);
+        int v;
+        if (kind == 1) {
+            v = (int)(int16_t)(uint16_t)(h & 0xffffu);
+        } else {
+            const uint32_t f1 = 40u + (uint32_t)(k & 0x3ffu);
+            const uint32_t f2 = 300u + (uint32_t)((k >> 10) & 0xfffu);
+            const int a1 = 2000 + (int)((k >> 22) & 0x1fffu);
+            const int a2 = 500 + (int)((k >> 35) & 0xfffu);
+            const uint32_t i32 = (uint32_t)i;
+            v = ((tri16(i32 * f1) * a1) >> 15) + ((tri16(i32 * f2) * a2) >> 15);
+            v += (int)(h >> 52) - 2048;
+            v = max(-32768, min(32767, v));
+        }
+        pcm[e] = (int16_t)v;
+    }
+}
+
+cudaError_t launch_gen_pcm(int16_t *d_pcm, uint64_t n_streams, uint64_t first_stream, uint32_t channels,
+                           uint64_t samples, uint64_t start, uint64_t seed, int kind, cudaStream_t s)
+{
+    if (n_streams == 0 || samples == 0 || channels == 0) return cudaSuccess;
+    gen_pcm_kernel<<<148 * 16, 256, 0, s>>>(d_pcm, n_streams, first_stream, channels, samples, start, seed, kind);
+    return cudaGetLastError();
+}
+
+// Valid .qoa streams with pseudo-random LMS states and slice words.  One thread per 8-byte word.
+__global__ void gen_qoa_kernel(uint8_t *__restrict__ qoa, uint64_t stride, uint64_t n_streams, uint64_t first_stream,
+                               uint32_t channels, uint32_t rate, uint32_t samples, uint64_t seed)
+{
+    const uint64_t frames = ((uint64_t)samples + kFrameLen - 1) / kFrameLen;
+    const uint64_t slices = ((uint64_t)samples + kSliceLen - 1) / kSliceLen;
+    const uint64_t words = 1 + frames * (1 + 2ull * channels) + slices * channels; // encoded size / 8 (:374-378)
+    const uint64_t wpf = 1 + 2ull * channels + (uint64_t)kSlicesPerFrame * channels;
+    const uint64_t total = n_streams * words;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = e / words;
+        const uint64_t j = e - s * words;
+        uint32_t hi, lo;
+        if (j == 0) {
+            hi = kMagic;
+            lo = samples;
+        } else {
+            const uint64_t f = (j - 1) / wpf;
+            const uint64_t r = (j - 1) - f * wpf;
+            if (r == 0) {
+                const uint32_t frame_len = (uint32_t)min((uint64_t)kFrameLen, (uint64_t)samples - f * kFrameLen);
+                const uint32_t nsl = (frame_len + kSliceLen - 1) / kSliceLen;
+                hi = (channels << 24) | rate;
+                lo = (frame_len << 16) | ((8 + 16 * channels + 8 * nsl * channels) & 0xffffu);
+            } else {
+                const uint64_t h = splitmix64(stream_key(seed, first_stream + s, 0) + j);
+                hi = (uint32_t)(h >> 32);
+                lo = (uint32_t)h;
+            }
+        }
+        st_be64(qoa + s * stride + j * 8, hi, lo);
+    }
+}
+
+cudaError_t launch_gen_qoa(uint8_t *d_qoa, uint64_t stride, uint64_t n_streams, uint64_t first_stream,
+                           uint32_t channels, uint32_t rate, uint32_t samples, uint64_t seed, cudaStream_t s)
+{
+    if (n_streams == 0 || samples == 0 || channels == 0) return cudaSuccess;
+    gen_qoa_kernel<<<148 * 16, 256, 0, s>>>(d_qoa, stride, n_streams, first_stream, channels, rate, samples, seed);
+    return cudaGetLastError();
+}
+
+// ---- integer issue-rate microbenchmark -----------------------------------------------------------------------
+// 8 independent dependency chains per thread, 16 warps per SM x 4 CTAs: enough to saturate every scheduler.
+template <int KIND>
+__global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int a, int b)
+{
+    int x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (KIND == 0 || KIND == 2) { // IMAD
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+            }
+            if (KIND == 0) {
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+            if (KIND == 1) { // LOP3
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(a), "r"(b));
+            }
+            if (KIND == 1 || KIND == 2) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+        }
+    }
+    const int r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+    if (r == 0x7fffffff) out[0] = r; // practically never; keeps the chains alive
+}
+
+cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
+{
+    int *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, sizeof(int));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int iters = 4096, grid = sm_count * 4, block = 512;
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(t0);
+        if (kind == 0) int_issue_kernel<0><<<grid, block>>>(d_out, iters, 3, 7);
+        else if (kind == 1) int_issue_kernel<1><<<grid, block>>>(d_out, iters, 3, 7);
+        else int_issue_kernel<2><<<grid, block>>>(d_out, iters, 3, 7);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return e;
+    const double ops = (double)grid * block * (double)iters * 64.0;
+    *thread_ops_per_s = ops / (best_ms * 1e-3);
+    return cudaGetLastError();
+}
+
+} // namespace qoa

@@ -1,0 +1,300 @@
+"""Engine: one context per GPU plus the batched host- and device-level calls over the C ABI.
+
+This is the host-side mirror of the reference's encoder/decoder objects for BATCHES of streams.  The per-stream,
+crate-shaped API (encode_all, QoaEncoder, QoaDecoder, ...) lives in api.py and is a thin layer over this module.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _native as N
+
+
+def _arr(values, ctype):
+    return (ctype * len(values))(*values)
+
+
+class Engine:
+    """Owns a qoa_b200_ctx on one CUDA device."""
+
+    def __init__(self, device=None):
+        if device is None:
+            device = int(os.environ.get("QOA_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        self.device = device
+        self._h = C.c_void_p()
+        rc = N.lib().qoa_b200_ctx_create(device, C.byref(self._h))
+        if rc != 0:
+            msg = N.lib().qoa_b200_last_error(None)
+            raise N.NativeError(f"qoa_b200_ctx_create(device={device}) failed with {rc}: {msg.decode()} "
+                                "(qoaudio_b200 has no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            N.lib().qoa_b200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def kernel_launches(self):
+        return int(N.lib().qoa_b200_kernel_launches(self._h))
+
+    # ---- encode, host buffers ------------------------------------------------------------------------------
+    def encode_all_batch(self, pcm_list, descs):
+        """Batched encode_all (src/lib.rs:760).  pcm_list[i]: int16 array (interleaved), descs[i]: (channels,
+        sample_rate, samples).  Returns (status list, list of bytes-like np.uint8 arrays)."""
+        n = len(pcm_list)
+        assert len(descs) == n
+        if n == 0:
+            return [], []
+        pcm = [np.ascontiguousarray(p, dtype=np.int16).reshape(-1) for p in pcm_list]
+        d = (N.Desc * n)(*[N.Desc(int(c), int(r), int(s)) for (c, r, s) in descs])
+        outs = []
+        for (c, r, s) in descs:
+            ok = 1 <= c <= 8 and r > 0 and s > 0
+            outs.append(np.empty(N.lib().qoa_b200_encoded_size(c, s) if ok else 0, dtype=np.uint8))
+        pcm_ptr = _arr([p.ctypes.data if p.size else None for p in pcm], C.c_void_p)
+        pcm_len = _arr([p.size for p in pcm], C.c_size_t)
+        out_ptr = _arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p)
+        out_cap = _arr([o.size for o in outs], C.c_size_t)
+        out_len = (C.c_size_t * n)()
+        status = (C.c_int32 * n)()
+        rc = N.lib().qoa_b200_encode_all_batch(self._h, d, pcm_ptr, pcm_len, out_ptr, out_cap, out_len, status, n)
+        N.check(self._h, rc, "qoa_b200_encode_all_batch")
+        return list(status), [o[:out_len[i]] for i, o in enumerate(outs)]
+
+    # ---- encode, device buffers -----------------------------------------------------------------------------
+    def encode_all_batch_dev(self, descs, d_pcm, pcm_off, pcm_len, d_out, out_off, out_cap, stream=0):
+        """Device-resident batched encode_all.  d_pcm/d_out: raw device pointers (int).  Returns (status, out_len)."""
+        n = len(descs)
+        d = (N.Desc * n)(*[N.Desc(int(c), int(r), int(s)) for (c, r, s) in descs])
+        out_len = (C.c_size_t * n)()
+        status = (C.c_int32 * n)()
+        rc = N.lib().qoa_b200_encode_all_batch_dev(self._h, d, C.c_void_p(d_pcm), _arr(pcm_off, C.c_uint64),
+                                                   _arr(pcm_len, C.c_size_t), C.c_void_p(d_out),
+                                                   _arr(out_off, C.c_uint64), _arr(out_cap, C.c_size_t), out_len,
+                                                   status, n, C.c_void_p(stream))
+        N.check(self._h, rc, "qoa_b200_encode_all_batch_dev")
+        return list(status), list(out_len)
+
+    def encoder_batch(self, descs):
+        return EncoderBatch(self, descs)
+
+    # ---- decode -----------------------------------------------------------------------------------------------
+    def decode_plan(self, streams, mode=N.DECODE_ITER):
+        """Index a batch of host-resident .qoa byte strings."""
+        return DecodePlan._from_host(self, streams, mode)
+
+    def decode_plan_dev(self, d_qoa, in_off, lens, mode=N.DECODE_ITER, stream=0):
+        return DecodePlan._from_dev(self, d_qoa, in_off, lens, mode, stream)
+
+    def decode_batch(self, streams, mode=N.DECODE_ITER):
+        """Decode host-resident streams.  Returns (infos, list of np.int16 arrays)."""
+        plan = self.decode_plan(streams, mode)
+        try:
+            return plan.info, plan.run()
+        finally:
+            plan.close()
+
+    # ---- generators / microbenchmarks --------------------------------------------------------------------------
+    def gen_pcm_dev(self, d_pcm, n_streams, first_stream, channels, samples, start, seed, kind="music", stream=0):
+        rc = N.lib().qoa_b200_gen_pcm_dev(self._h, C.c_void_p(d_pcm), n_streams, first_stream, channels, samples, start,
+                                          seed, 1 if kind == "noise" else 0, C.c_void_p(stream))
+        N.check(self._h, rc, "qoa_b200_gen_pcm_dev")
+
+    def gen_qoa_dev(self, d_qoa, stride, n_streams, first_stream, channels, sample_rate, samples, seed, stream=0):
+        rc = N.lib().qoa_b200_gen_qoa_dev(self._h, C.c_void_p(d_qoa), stride, n_streams, first_stream, channels,
+                                          sample_rate, samples, seed, C.c_void_p(stream))
+        N.check(self._h, rc, "qoa_b200_gen_qoa_dev")
+
+    def int_issue_peak(self, kind):
+        v = C.c_double(0)
+        rc = N.lib().qoa_b200_int_issue_peak(self._h, kind, C.byref(v))
+        N.check(self._h, rc, "qoa_b200_int_issue_peak")
+        return v.value
+
+
+class EncoderBatch:
+    """Batch of streaming encoders: QoaEncoder::{new, write_header, encode_frame} (src/lib.rs:335, :404, :418)."""
+
+    def __init__(self, engine, descs):
+        self.engine = engine
+        self.descs = [(int(c), int(r), int(s)) for (c, r, s) in descs]
+        n = len(self.descs)
+        d = (N.Desc * n)(*[N.Desc(c, r, s) for (c, r, s) in self.descs])
+        st = (C.c_int32 * n)()
+        self._h = C.c_void_p()
+        rc = N.lib().qoa_b200_encoder_batch_new(engine.handle, d, n, st, C.byref(self._h))
+        N.check(engine.handle, rc, "qoa_b200_encoder_batch_new")
+        self.status = list(st)
+
+    def close(self):
+        if self._h:
+            N.lib().qoa_b200_encoder_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def write_header(self):
+        n = len(self.descs)
+        bufs = [np.zeros(8, dtype=np.uint8) for _ in range(n)]
+        rc = N.lib().qoa_b200_encoder_batch_write_header(self._h, _arr([b.ctypes.data for b in bufs], C.c_void_p))
+        N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_write_header")
+        return [b.tobytes() for b in bufs]
+
+    def encode_frame(self, pcm_list):
+        """pcm_list[i]: int16 array for stream i's next frame, or None to skip the stream this round.
+        Returns (status list, list of bytes)."""
+        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_frame, None)
+
+    def encode_chunk(self, pcm_list):
+        """Like encode_frame but any number of samples per stream (cut into frames of 5120)."""
+        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_chunk, "chunk")
+
+    def _encode_host(self, pcm_list, fn, kind):
+        n = len(self.descs)
+        assert len(pcm_list) == n
+        pcm = [None if p is None else np.ascontiguousarray(p, dtype=np.int16).reshape(-1) for p in pcm_list]
+        if kind == "chunk":
+            caps = [0 if p is None or c == 0 else N.lib().qoa_b200_encoded_size(c, -(-p.size // c)) for p, (c, _, _) in
+                    zip(pcm, self.descs)]
+        else:
+            caps = [8 + 16 * 8 + 8 * 256 * 8] * n
+        outs = [np.empty(max(c, 8), dtype=np.uint8) for c in caps]
+        written = (C.c_size_t * n)()
+        status = (C.c_int32 * n)()
+        dummy = np.zeros(1, dtype=np.int16)  # a non-NULL pointer for "fed an empty frame" (-> InvalidSamples)
+        ptrs = [None if p is None else (p.ctypes.data if p.size else dummy.ctypes.data) for p in pcm]
+        rc = fn(self._h, _arr(ptrs, C.c_void_p), _arr([0 if p is None else p.size for p in pcm], C.c_size_t),
+                _arr([o.ctypes.data for o in outs], C.c_void_p), _arr([o.size for o in outs], C.c_size_t), written,
+                status)
+        N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_encode_frame/chunk")
+        return list(status), [outs[i][:written[i]].tobytes() for i in range(n)]
+
+    def encode_chunk_dev(self, d_pcm, pcm_off, chunk_samples, d_out, out_off, stream=0):
+        rc = N.lib().qoa_b200_encoder_batch_encode_chunk_dev(
+            self._h, C.c_void_p(d_pcm), _arr(pcm_off, C.c_uint64), _arr(chunk_samples, C.c_uint32), C.c_void_p(d_out),
+            _arr(out_off, C.c_uint64), C.c_void_p(stream))
+        N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_encode_chunk_dev")
+
+    def lms(self, i, c):
+        h = (C.c_int32 * 4)()
+        w = (C.c_int32 * 4)()
+        rc = N.lib().qoa_b200_encoder_batch_get_lms(self._h, i, c, h, w)
+        N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_get_lms")
+        return list(h), list(w)
+
+
+class DecodePlan:
+    """Frame index of a batch (the validation pre-pass) + decode."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self.engine = None
+        self.n = 0
+        self.info = []
+        self._keep = None
+
+    @staticmethod
+    def _info_list(h, n):
+        arr = (N.StreamInfo * max(n, 1))()
+        N.lib().qoa_b200_decode_plan_info(h, arr)
+        return [dict(status=a.status, streaming=bool(a.streaming), header_samples=a.header_samples, channels=a.channels,
+                     sample_rate=a.sample_rate, samples=int(a.samples), frames=int(a.frames),
+                     index_frames=a.index_frames, max_channels=a.max_channels, flags=a.flags) for a in arr[:n]]
+
+    @classmethod
+    def _from_host(cls, engine, streams, mode):
+        self = cls()
+        self.engine = engine
+        bufs = [np.frombuffer(bytes(s), dtype=np.uint8) if not isinstance(s, np.ndarray)
+                else np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
+        n = len(bufs)
+        self.n = n
+        self._keep = bufs
+        rc = N.lib().qoa_b200_decode_plan_create(
+            engine.handle, _arr([b.ctypes.data if b.size else None for b in bufs], C.c_void_p),
+            _arr([b.size for b in bufs], C.c_size_t), n, mode, C.byref(self._h))
+        N.check(engine.handle, rc, "qoa_b200_decode_plan_create")
+        self.info = cls._info_list(self._h, n)
+        return self
+
+    @classmethod
+    def _from_dev(cls, engine, d_qoa, in_off, lens, mode, stream):
+        self = cls()
+        self.engine = engine
+        n = len(lens)
+        self.n = n
+        rc = N.lib().qoa_b200_decode_plan_create_dev(engine.handle, C.c_void_p(d_qoa), _arr(in_off, C.c_uint64),
+                                                     _arr(lens, C.c_size_t), n, mode, C.c_void_p(stream),
+                                                     C.byref(self._h))
+        N.check(engine.handle, rc, "qoa_b200_decode_plan_create_dev")
+        self.info = cls._info_list(self._h, n)
+        return self
+
+    def close(self):
+        if self._h:
+            N.lib().qoa_b200_decode_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def frame_headers(self, i):
+        cnt = self.info[i]["index_frames"]
+        arr = (N.FrameHeaderC * max(cnt, 1))()
+        got = N.lib().qoa_b200_decode_plan_frame_headers(self._h, i, arr, cnt)
+        return [(a.num_channels, a.sample_rate, a.num_samples_per_channel) for a in arr[:min(got, cnt)]]
+
+    def run(self, caps=None):
+        """Decode into fresh host arrays.  Returns list of np.int16 arrays (what the iterator yields as samples)."""
+        n = self.n
+        if n == 0:
+            return []
+        if caps is None:
+            caps = [inf["samples"] for inf in self.info]
+        outs = [np.empty(c, dtype=np.int16) for c in caps]
+        status = (C.c_int32 * n)()
+        rc = N.lib().qoa_b200_decode_plan_run(self._h, _arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p),
+                                              _arr(caps, C.c_size_t), status)
+        N.check(self.engine.handle, rc, "qoa_b200_decode_plan_run")
+        self.run_status = list(status)
+        return [o[:min(self.info[i]["samples"], caps[i])] if status[i] != N.DEC_OUTPUT_TOO_SMALL else o[:0]
+                for i, o in enumerate(outs)]
+
+    def run_dev(self, d_out, out_off, out_cap, stream=0):
+        n = self.n
+        status = (C.c_int32 * max(n, 1))()
+        rc = N.lib().qoa_b200_decode_plan_run_dev(self._h, C.c_void_p(d_out), _arr(out_off, C.c_uint64),
+                                                  _arr(out_cap, C.c_size_t), status, C.c_void_p(stream))
+        N.check(self.engine.handle, rc, "qoa_b200_decode_plan_run_dev")
+        return list(status[:n])
+
+
+_default = None
+_lock = threading.Lock()
+
+
+def default_engine():
+    """Process-wide engine on device QOA_B200_DEVICE / LOCAL_RANK / 0 (one process per GPU)."""
+    global _default
+    with _lock:
+        if _default is None:
+            _default = Engine()
+        return _default

@@ -1,0 +1,371 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+and the committed golden vectors.  Bit-exact: identical .qoa bytes on encode, identical i16 samples on decode."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import signals
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import qoaudio_b200
+    return qoaudio_b200.default_engine()
+
+
+@pytest.fixture(scope="module")
+def N():
+    import qoaudio_b200._native as n
+    return n
+
+
+INFO_KEYS = ("status", "streaming", "header_samples", "channels", "sample_rate", "samples", "frames")
+
+
+def oracle_info(data, mode):
+    if mode == 0:
+        info, pcm, _ = ob.decode_iter(data)
+    else:
+        info, pcm = ob.decode_all(data)
+    return info, pcm
+
+
+def check_decode_batch(eng, streams, mode):
+    infos, outs = eng.decode_batch(streams, mode)
+    for i, s in enumerate(streams):
+        oi, opcm = oracle_info(s, mode)
+        got = {k: infos[i][k] for k in INFO_KEYS}
+        assert got == oi, (i, len(s), got, oi)
+        assert np.array_equal(outs[i], opcm), (i, "samples differ")
+
+
+# ---- config 1: the reference fixture -----------------------------------------------------------------------------
+
+def test_fixture_decode_matches_golden(eng, fixture_bytes, golden):
+    infos, outs = eng.decode_batch([fixture_bytes], 0)
+    info = infos[0]
+    assert info["status"] == 0 and not info["streaming"]
+    assert (info["channels"], info["sample_rate"], info["header_samples"]) == (2, 44100, 2394122)  # src/lib.rs:1005-1012
+    assert info["frames"] == 468 and info["samples"] == 2394122 * 2                                   # :1018-1031
+    assert sha(outs[0].tobytes()) == golden["appendix_b"]["fixture_decoded_pcm_sha256"]
+    _, opcm, _ = ob.decode_iter(fixture_bytes)
+    assert np.array_equal(outs[0], opcm)
+
+
+def test_fixture_reencode_matches_golden(eng, fixture_bytes, golden):
+    _, pcm, _ = ob.decode_iter(fixture_bytes)
+    st, outs = eng.encode_all_batch([pcm], [(2, 44100, 2394122)])
+    assert st == [0]
+    assert len(outs[0]) == 1934040
+    assert sha(outs[0].tobytes()) == golden["appendix_b"]["fixture_reencode_sha256"]
+    infos, dec = eng.decode_batch([outs[0].tobytes()], 1)
+    assert sha(dec[0].tobytes()) == golden["appendix_b"]["fixture_reencode_decoded_sha256"]
+
+
+# ---- known-answer encodes ---------------------------------------------------------------------------------------------
+
+def test_kat_encodes(eng, golden):
+    kats = signals.kat_signals()
+    names = sorted(kats)
+    st, outs = eng.encode_all_batch([kats[k][0] for k in names], [kats[k][1:] for k in names])
+    assert st == [0] * len(names)
+    for k, o in zip(names, outs):
+        g = golden["appendix_b"]["kats"][k]
+        assert len(o) == g["len"], k
+        assert sha(o.tobytes()) == g["sha256"], k
+        ost, obytes = ob.encode_all(kats[k][0], *kats[k][1:])
+        assert o.tobytes() == obytes
+
+
+def test_edge_signals_all_channel_counts(eng):
+    pcm_list, descs = [], []
+    for name, sig in signals.edge_signals().items():
+        for ch in range(1, 9):
+            n = sig.size // ch
+            if n == 0:
+                continue
+            pcm_list.append(sig[:n * ch])
+            descs.append((ch, 8000 + 1000 * ch, n))
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * len(descs)
+    for p, d, o in zip(pcm_list, descs, outs):
+        ost, obytes = ob.encode_all(p, *d)
+        assert ost == 0 and o.tobytes() == obytes, d
+    check_decode_batch(eng, [o.tobytes() for o in outs], 0)
+    check_decode_batch(eng, [o.tobytes() for o in outs], 1)
+
+
+# ---- config 5: mixed batch --------------------------------------------------------------------------------------------
+
+def mixed_batch(count=64, seed=1, long_every=16):
+    rates = [8000, 11025, 16000, 22050, 32000, 44100, 48000, 96000]
+    lengths = [1, 19, 20, 21, 39, 40, 41, 5119, 5120, 5121, 10259, 12345]
+    pcm_list, descs = [], []
+    for i in range(count):
+        ch = i % 8 + 1
+        rate = rates[(i // 8) % len(rates)]
+        n = lengths[(i * 7 + i // 8) % len(lengths)]
+        if long_every and i % long_every == long_every - 1:
+            n = 123457 // ch
+        kind = "noise" if i % 5 == 4 else "music"
+        pcm_list.append(signals.synth_pcm(seed, i, ch, n, kind))
+        descs.append((ch, rate, n))
+    return pcm_list, descs
+
+
+def test_mixed_batch_roundtrip(eng):
+    pcm_list, descs = mixed_batch()
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * len(descs)
+    enc = []
+    for p, d, o in zip(pcm_list, descs, outs):
+        ost, obytes = ob.encode_all(p, *d)
+        assert ost == 0
+        assert len(o) == len(obytes), d
+        assert o.tobytes() == obytes, d
+        enc.append(obytes)
+    infos, dec = eng.decode_batch(enc, 1)
+    for i, (d, e) in enumerate(zip(descs, enc)):
+        oi, opcm = ob.decode_all(e)
+        assert infos[i]["status"] == 0 and infos[i]["samples"] == d[0] * d[2]
+        assert (infos[i]["channels"], infos[i]["sample_rate"]) == (d[0], d[1])
+        assert np.array_equal(dec[i], opcm), d
+
+
+def test_stereo_batch_fast_path(eng):
+    """All-stereo batches take the fast stereo kernel: full frames, partial last frames and partial last slices."""
+    lens = [5120, 5120 * 3, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 4080, 2 * 5120 + 3082]
+    pcm_list = [signals.synth_pcm(3, i, 2, n) for i, n in enumerate(lens)]
+    descs = [(2, 44100, n) for n in lens]
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * len(lens)
+    enc = [o.tobytes() for o in outs]
+    for p, d, e in zip(pcm_list, descs, enc):
+        assert e == ob.encode_all(p, *d)[1]
+    check_decode_batch(eng, enc, 0)
+
+
+def test_noise_brute_equivalence(eng):
+    """White noise is the worst case for the reference's pruning; the GPU's full search must pick the same winners."""
+    pcm = signals.synth_pcm(2, 5, 2, 30000, "noise")
+    st, outs = eng.encode_all_batch([pcm], [(2, 48000, 30000)])
+    assert st == [0]
+    assert outs[0].tobytes() == ob.encode_all(pcm, 2, 48000, 30000)[1]
+    assert outs[0].tobytes() == ob.encode_all(pcm, 2, 48000, 30000, brute=True)[1]
+
+
+# ---- encoder errors and streaming ------------------------------------------------------------------------------------
+
+def test_encoder_errors(eng, N):
+    """src/lib.rs:1148-1183 + :368 + precedence :336-344."""
+    z = np.zeros(10, dtype=np.int16)
+    descs = [(0, 44100, 10), (9, 44100, 10), (1, 0, 10), (1, 44100, 0), (0, 0, 0), (2, 0, 0), (1, 44100, 11), (1, 44100, 10)]
+    st, outs = eng.encode_all_batch([z] * len(descs), descs)
+    assert st == [N.ENC_INVALID_CHANNELS, N.ENC_INVALID_CHANNELS, N.ENC_INVALID_SAMPLE_RATE, N.ENC_INVALID_SAMPLES,
+                  N.ENC_INVALID_CHANNELS, N.ENC_INVALID_SAMPLE_RATE, N.ENC_INVALID_SAMPLES, 0]
+    for d, s in zip(descs, st):
+        ost, _ = ob.encode_all(z, *d)
+        assert ost == s
+    assert outs[-1].tobytes() == ob.encode_all(z, 1, 44100, 10)[1]
+
+
+def test_streaming_encode_equals_one_shot(eng):
+    """src/lib.rs:1261-1297, for a batch of differently shaped streams; also checks the carried i32 LMS state."""
+    shapes = [(1, 44100, 5120 * 2 + 777), (2, 48000, 5120 * 3), (3, 8000, 5120 + 1), (8, 96000, 5120 * 2 + 19)]
+    pcm_list = [signals.synth_pcm(9, i, c, n, "noise" if i == 2 else "music") for i, (c, r, n) in enumerate(shapes)]
+    st, one_shot = eng.encode_all_batch(pcm_list, shapes)
+    assert st == [0] * len(shapes)
+    batch = eng.encoder_batch(shapes)
+    assert batch.status == [0] * len(shapes)
+    streams = [bytearray(h) for h in batch.write_header()]
+    oracles = [ob.StreamEncoder(*s) for s in shapes]
+    rounds = max((n + 5119) // 5120 for (_, _, n) in shapes)
+    for r in range(rounds):
+        frames = []
+        for (c, _, n), p in zip(shapes, pcm_list):
+            lo, hi = r * 5120, min(n, (r + 1) * 5120)
+            frames.append(p[lo * c:hi * c] if lo < n else None)
+        fst, outs = batch.encode_frame(frames)
+        for i, f in enumerate(frames):
+            if f is None:
+                assert outs[i] == b""
+                continue
+            assert fst[i] == 0
+            ost, obytes = oracles[i].encode_frame(f)
+            assert outs[i] == obytes
+            streams[i] += outs[i]
+            for c in range(shapes[i][0]):
+                assert batch.lms(i, c) == tuple(oracles[i].lms(c))
+    for s, o in zip(streams, one_shot):
+        assert bytes(s) == o.tobytes()
+    batch.close()
+
+
+def test_encode_frame_errors(eng, N):
+    """src/lib.rs:424-430"""
+    batch = eng.encoder_batch([(2, 44100, 100), (2, 44100, 100), (2, 44100, 100), (0, 1, 1)])
+    assert batch.status == [0, 0, 0, N.ENC_INVALID_CHANNELS]
+    st, outs = batch.encode_frame([np.zeros(0, np.int16), np.zeros(3, np.int16), np.zeros(5121 * 2, np.int16),
+                                   np.zeros(2, np.int16)])
+    assert st == [N.ENC_INVALID_SAMPLES] * 3 + [N.ENC_INVALID_CHANNELS]
+    assert outs == [b""] * 4
+    batch.close()
+
+
+# ---- decoder: malformed / foreign inputs -----------------------------------------------------------------------------
+
+def small_file(ch=2, n=45, rate=8000, seed=4):
+    pcm = signals.synth_pcm(seed, 0, ch, n)
+    st, b = ob.encode_all(pcm, ch, rate, n)
+    assert st == 0
+    return b
+
+
+def test_truncated_inputs_every_length(eng):
+    data = small_file(ch=2, n=45) + small_file(ch=2, n=45)[8:]  # two frames
+    cuts = [data[:k] for k in range(len(data) + 1)]
+    check_decode_batch(eng, cuts, 0)
+    check_decode_batch(eng, cuts, 1)
+    big = small_file(ch=3, n=5120 + 30, rate=44100)
+    cuts = [big[:k] for k in list(range(0, 80)) + list(range(len(big) - 200, len(big) + 1)) + [24632, 24640, 24641]]
+    check_decode_batch(eng, cuts, 0)
+
+
+def be64(v):
+    return int(v).to_bytes(8, "big")
+
+
+def frame(ch, rate, nspc, seed=0, frame_size=None, slices=None):
+    """A hand-built frame with pseudo-random LMS and slices."""
+    nsl = (nspc + 19) // 20 if slices is None else slices
+    fs = 8 + 16 * ch + 8 * nsl * ch if frame_size is None else frame_size
+    rng = np.random.default_rng(seed)
+    body = rng.integers(0, 256, size=16 * ch + 8 * nsl * ch, dtype=np.uint8).tobytes()
+    return be64((ch << 56) | (rate << 32) | (nspc << 16) | (fs & 0xffff)) + body
+
+
+def header(samples):
+    return b"qoaf" + int(samples).to_bytes(4, "big")
+
+
+def test_malformed_headers(eng):
+    f = frame(2, 44100, 40, 1)
+    cases = [
+        b"", b"qoa", b"qoaf", b"qoag\0\0\0\1", b"qoaf\0\0\0", header(40),                  # IoError/NotQoaFile/NoSamples
+        header(40) + f,                                                                       # ok
+        header(40) + frame(0, 44100, 40), header(40) + frame(2, 0, 40),                      # :227
+        header(40) + frame(2, 44100, 40, frame_size=8 + 32),                                  # :233
+        header(40) + frame(2, 44100, 40, frame_size=8 + 32 + 8 * 3),                          # :239
+        header(40) + frame(1, 44100, 5120, frame_size=8 + 16 + 8 * 257, slices=257),          # :242
+        header(40) + f + frame(1, 44100, 40, 2),                                              # IncompatibleFrame (channels)
+        header(40) + f + frame(2, 48000, 40, 2),                                              # IncompatibleFrame (rate)
+        header(40) + f + b"\1\2\3",                                                           # trailing junk < 8: clean EOF
+        header(40) + f + frame(2, 44100, 0, 3, frame_size=8 + 32 + 16) + frame(2, 44100, 25, 4),  # nspc == 0 frame
+        header(0) + f + frame(3, 48000, 25, 5) + frame(1, 8000, 1, 6),                        # streaming file: changes allowed
+        header(0),                                                                            # streaming, no frames
+        header(99) + frame(2, 44100, 40, 7, frame_size=8 + 32 + 16 * 5) + f,                  # frame_size ignored for walking
+        header(40) + frame(2, 44100, 65535, 8, frame_size=8 + 32 + 16, slices=3277)[:4000],   # huge nspc, truncated
+        header(40) + frame(255, 16777215, 21, 9, frame_size=(8 + 16 * 255 + 16 * 255) & 0xffff),  # 255 channels
+        header(7) + frame(2, 44100, 3, 10) + frame(2, 44100, 4, 11),                          # odd-length interior frame
+    ]
+    check_decode_batch(eng, cases, 0)
+    check_decode_batch(eng, cases, 1)
+
+
+def test_streaming_decode_frames(eng, fixture_bytes, N):
+    """src/lib.rs:1034-1066: new_streaming + decode_frame on the first two fixture frames."""
+    pos = 8
+    frames = []
+    for _ in range(3):
+        size = int.from_bytes(fixture_bytes[pos + 6:pos + 8], "big")
+        frames.append(fixture_bytes[pos:pos + size])
+        pos += size
+    infos, outs = eng.decode_batch(frames + [frames[0] + frames[1]], N.DECODE_FRAMES)
+    sd = ob.StreamDecoder()
+    for i in range(3):
+        st, opcm = sd.decode_frame(frames[i])
+        assert st == 0 and infos[i]["status"] == 0
+        assert outs[i].size == 5120 * 2
+        assert np.array_equal(outs[i], opcm)
+    assert np.array_equal(outs[3], np.concatenate([outs[0], outs[1]]))
+
+
+# ---- generators --------------------------------------------------------------------------------------------------------
+
+def test_gen_pcm_matches_numpy(eng):
+    import torch
+    for kind in ("music", "noise"):
+        for ch, n, start in ((2, 1000, 0), (3, 777, 12345), (1, 64, 2 ** 33 + 5)):
+            t = torch.empty(4 * ch * n, dtype=torch.int16, device="cuda")
+            eng.gen_pcm_dev(t.data_ptr(), 4, 10, ch, n, start, 7, kind)
+            torch.cuda.synchronize()
+            got = t.cpu().numpy().reshape(4, -1)
+            for s in range(4):
+                assert np.array_equal(got[s], signals.synth_pcm(7, 10 + s, ch, n, kind, start)), (kind, ch, n, s)
+
+
+def test_gen_qoa_decodes_like_oracle(eng):
+    import torch
+    ch, rate, n = 2, 44100, 5120 * 2 + 4080
+    size = ob.encoded_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    t = torch.zeros(3 * stride, dtype=torch.uint8, device="cuda")
+    eng.gen_qoa_dev(t.data_ptr(), stride, 3, 0, ch, rate, n, 1)
+    torch.cuda.synchronize()
+    host = t.cpu().numpy()
+    streams = [host[i * stride:i * stride + size].tobytes() for i in range(3)]
+    assert len(set(streams)) == 3
+    check_decode_batch(eng, streams, 0)
+    # the same through the device-resident API
+    plan = eng.decode_plan_dev(t.data_ptr(), [i * stride for i in range(3)], [size] * 3, 1)
+    out = torch.zeros(3 * n * ch, dtype=torch.int16, device="cuda")
+    st = plan.run_dev(out.data_ptr(), [i * n * ch for i in range(3)], [n * ch] * 3)
+    torch.cuda.synchronize()
+    assert st == [0, 0, 0]
+    got = out.cpu().numpy().reshape(3, -1)
+    for i in range(3):
+        assert np.array_equal(got[i], ob.decode_all(streams[i])[1])
+    plan.close()
+
+
+def test_device_encode_chunked_equals_one_shot(eng):
+    """Time-chunked device-resident encode with persistent LMS state (the config-4 path) == encode_all."""
+    import torch
+    n_streams, ch, rate, n = 6, 2, 48000, 5120 * 5 + 2560
+    pcm = torch.empty(n_streams * ch * n, dtype=torch.int16, device="cuda")
+    eng.gen_pcm_dev(pcm.data_ptr(), n_streams, 100, ch, n, 0, 1, "music")
+    size = ob.encoded_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    out = torch.zeros(n_streams * stride, dtype=torch.uint8, device="cuda")
+    st, lens = eng.encode_all_batch_dev([(ch, rate, n)] * n_streams, pcm.data_ptr(), [i * ch * n for i in range(n_streams)],
+                                        [ch * n] * n_streams, out.data_ptr(), [i * stride for i in range(n_streams)],
+                                        [stride] * n_streams)
+    torch.cuda.synchronize()
+    assert st == [0] * n_streams and lens == [size] * n_streams
+    one = out.cpu().numpy().reshape(n_streams, stride)[:, :size]
+    host_pcm = pcm.cpu().numpy().reshape(n_streams, -1)
+    for i in range(n_streams):
+        assert np.array_equal(host_pcm[i], signals.synth_pcm(1, 100 + i, ch, n))
+        assert one[i].tobytes() == ob.encode_all(host_pcm[i], ch, rate, n)[1]
+    # chunked: 2 frames per call
+    out2 = torch.zeros(n_streams * stride, dtype=torch.uint8, device="cuda")
+    batch = eng.encoder_batch([(ch, rate, n)] * n_streams)
+    fbytes = 8 + 16 * ch + 2048 * ch
+    done = 0
+    while done < n:
+        step = min(2 * 5120, n - done)
+        batch.encode_chunk_dev(pcm.data_ptr(), [i * ch * n + done * ch for i in range(n_streams)], [step] * n_streams,
+                               out2.data_ptr(), [i * stride + 8 + (done // 5120) * fbytes for i in range(n_streams)])
+        done += step
+    torch.cuda.synchronize()
+    two = out2.cpu().numpy().reshape(n_streams, stride)[:, 8:size]
+    assert np.array_equal(two, one[:, 8:])
+    batch.close()
