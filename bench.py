@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — batch QOA decode/encode throughput on B200 (BASELINE.json metric: Msamples/s + roofline fraction).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One JSON line on stdout (rank 0).  Headline workload (config.workload) = BASELINE.json configs[2]:
+batch decode of 8192 synthetic stereo 44.1 kHz 60 s .qoa streams PER GPU (weak scaling: streams are independent,
+sharded by stream, no collective).  A "step" = index pre-pass + frame-parallel decode of the whole resident batch.
+The same line carries an "encode" object: configs[3]'s shape (4096 stereo 48 kHz streams per GPU) encoded in time
+chunks with the LMS state persistent on the device, a step = one chunk of --enc-frames frames of every stream.
+
+  value        device-resident throughput (inputs in HBM, CUDA events on the launching stream, max over ranks)
+  e2e          the same metric through the C-ABI call with HOST (pinned) buffers, H2D + D2H inside the timed region
+  roofline     decode kernel: algorithmic bytes / kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the CPU oracle (a C restatement of the reference crate; the crate itself needs rustc, absent here),
+               one stream per thread on the host cores, on a bounded sample of the same workload
+`--impl reference` times that CPU oracle alone, with all host threads, on the same config/metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DEC_CH, DEC_RATE, DEC_SAMPLES = 2, 44100, 2646000          # configs[2]: 60 s stereo 44.1 kHz
+ENC_CH, ENC_RATE, ENC_SAMPLES = 2, 48000, 14400000         # configs[3]: 5 min stereo 48 kHz
+ENC_OPS_PER_SAMPLE = 944                                   # 16 candidates x 59 integer ops
+
+
+def enc_size(ch, n):
+    return 8 + ((n + 5119) // 5120) * (8 + 16 * ch) + ((n + 19) // 20) * 8 * ch
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU during the timed region (pynvml, every 20 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference(args, want_encode=True):
+    """The CPU arm: oracle (kind 'port'), one stream per thread, bounded sample of the decode (and encode) workload."""
+    import numpy as np
+
+    import signals
+    from oracle import binding as ob
+    cores = os.cpu_count() or 1
+    threads = cores
+    # ---- decode sample: real encoder output of `threads` distinct 60 s streams would cost minutes of CPU encode;
+    # decode cost is data-independent, so the sample is built like the GPU's generator: valid headers + random payload.
+    n_dec = max(256, threads * 2)  # ~20 core-seconds of CPU work
+    size = enc_size(DEC_CH, DEC_SAMPLES)
+    rng = np.random.default_rng(1)
+    proto = np.frombuffer(rng.bytes(size), dtype=np.uint8).copy()
+    proto[0:8] = np.frombuffer(b"qoaf" + DEC_SAMPLES.to_bytes(4, "big"), dtype=np.uint8)
+    fsz = 8 + 16 * DEC_CH + 2048 * DEC_CH
+    frames = (DEC_SAMPLES + 5119) // 5120
+    for f in range(frames):
+        flen = min(5120, DEC_SAMPLES - f * 5120)
+        fs = 8 + 16 * DEC_CH + 8 * DEC_CH * ((flen + 19) // 20)
+        hdr = (DEC_CH << 56) | (DEC_RATE << 32) | (flen << 16) | fs
+        proto[8 + f * fsz:16 + f * fsz] = np.frombuffer(hdr.to_bytes(8, "big"), dtype=np.uint8)
+    batch = np.tile(proto, threads)
+    rounds = max(1, n_dec // threads)
+    out_stride = DEC_SAMPLES * DEC_CH
+    rc, _ = ob.mt_decode(batch, threads, size, out_stride, threads)  # warm-up (page faults)
+    assert rc == 0
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        rc, _ = ob.mt_decode(batch, threads, size, out_stride, threads)
+        assert rc == 0
+    dt = time.perf_counter() - t0
+    dec = {"value": rounds * threads * out_stride / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+           "sample": f"{rounds * threads} streams of the headline shape (60 s stereo 44.1 kHz, synthetic payload), "
+                     f"one stream per thread, {dt:.1f} s wall"}
+    enc = None
+    if want_encode:
+        n = 5120 * 40  # 4.3 s of the 48 kHz stereo shape per stream
+        pcm = np.concatenate([signals.synth_pcm(1, s, ENC_CH, n) for s in range(threads)])
+        rc, _ = ob.mt_encode(pcm, threads, ENC_CH, ENC_RATE, n, threads)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 8.0:
+            rc, _ = ob.mt_encode(pcm, threads, ENC_CH, ENC_RATE, n, threads)
+            assert rc == 0
+            reps += 1
+        dt = time.perf_counter() - t0
+        enc = {"value": reps * threads * n * ENC_CH / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+               "sample": f"{reps}x{threads} streams x {n} samples/ch stereo 48 kHz ('music' synthetic PCM, seed 1), "
+                         f"reference search order with pruning, {dt:.1f} s wall"}
+    return dec, enc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), args.warmup
+    # each step = the bounded decode sample; keep the whole run within a few minutes
+    vals = []
+    dec = None
+    for i in range(warm + steps):
+        dec, _ = cpu_reference(args, want_encode=False)
+        if i >= warm:
+            vals.append(dec["value"])
+        if len(vals) >= 3 and i >= warm + 2:
+            break
+    v = statistics.mean(vals)
+    dec["value"] = v
+    line = {"impl": "reference", "metric": "batch decode throughput", "value": v, "unit": "Msamples/s",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": warm,
+            "ms_per_step": DEC_SAMPLES * DEC_CH * max(256, 2 * (os.cpu_count() or 1)) / v / 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": workload_config(args), "cpu_baseline": dec,
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"batch decode {args.streams} synthetic stereo 44.1 kHz 60 s .qoa streams per GPU "
+                        "(BASELINE.json configs[2]), frame-parallel",
+            "streams_per_gpu": args.streams, "channels": DEC_CH, "sample_rate": DEC_RATE,
+            "samples_per_channel": DEC_SAMPLES, "l2": "inputs (2.1 MB x streams) larger than L2; no flush needed",
+            "sharding": "streams across ranks, no collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=8192, help="decode streams per GPU")
+    ap.add_argument("--enc-streams", type=int, default=4096, help="encode streams per GPU")
+    ap.add_argument("--enc-frames", type=int, default=16, help="frames per stream per encode step (time chunk)")
+    ap.add_argument("--e2e-streams", type=int, default=128)
+    ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import qoaudio_b200 as q
+    eng = q.Engine(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- decode (headline) -------------------------
+    S = args.streams
+    size = enc_size(DEC_CH, DEC_SAMPLES)
+    stride = (size + 15) // 16 * 16
+    out_per = DEC_SAMPLES * DEC_CH
+    qoa = torch.empty(S * stride, dtype=torch.uint8, device=dev)
+    pcm = torch.empty(S * out_per, dtype=torch.int16, device=dev)
+    eng.gen_qoa_dev(qoa.data_ptr(), stride, S, rank * S, DEC_CH, DEC_RATE, DEC_SAMPLES, 1, stream)
+    import numpy as np
+    in_off = np.arange(S, dtype=np.uint64) * np.uint64(stride)
+    lens = np.full(S, size, dtype=np.uint64)
+    out_off = np.arange(S, dtype=np.uint64) * np.uint64(out_per)
+    caps = np.full(S, out_per, dtype=np.uint64)
+
+    def decode_step(events=None):
+        plan = eng.decode_plan_dev(qoa.data_ptr(), in_off, lens, q._native.DECODE_ALL, stream)
+        if events is not None:
+            events[0].record()
+        st = plan.run_dev(pcm.data_ptr(), out_off, caps, stream)
+        if events is not None:
+            events[1].record()
+        info = plan.info_array
+        plan.close()
+        return st, info
+
+    for _ in range(W):
+        st, info = decode_step()
+    torch.cuda.synchronize()
+    assert (st == 0).all() and (info["samples"] == out_per).all() and (info["status"] == 0).all()
+    sampler = ClockSampler(local)
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.kernel_launches()
+    barrier()
+    sampler.start()
+    e0.record()
+    for k in range(K):
+        decode_step(kern_ev[k])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.kernel_launches() - launches0
+    dec_ms = reduce_max(e0.elapsed_time(e1))
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in kern_ev)
+    dec_samples_per_step = S * out_per * world
+    dec_value = dec_samples_per_step * K / (dec_ms * 1e-3) / 1e6
+    alg_bytes = S * (size + 2 * out_per)
+    # spot parity inside the bench: first and last stream of this rank vs the oracle (checker only, untimed)
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import binding as ob
+        for s in (0, S - 1):
+            blob = qoa[s * stride:s * stride + size].cpu().numpy().tobytes()
+            got = pcm[s * out_per:(s + 1) * out_per].cpu().numpy()
+            _, ref = ob.decode_all(blob)
+            assert np.array_equal(got, ref), f"bench decode of stream {s} differs from the oracle"
+        parity = "streams 0 and last bit-exact vs oracle"
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C ABI -------
+    e2e = None
+    if not args.no_e2e:
+        E = min(args.e2e_streams, S)
+        h_in = qoa[:E * stride].cpu().pin_memory()
+        h_out = torch.empty(E * out_per, dtype=torch.int16).pin_memory()
+        import ctypes as C
+        N = q._native
+        in_ptrs = (C.c_void_p * E)(*[h_in.data_ptr() + i * stride for i in range(E)])
+        in_lens = (C.c_size_t * E)(*([size] * E))
+        out_ptrs = (C.c_void_p * E)(*[h_out.data_ptr() + 2 * i * out_per for i in range(E)])
+        out_caps = (C.c_size_t * E)(*([out_per] * E))
+        stat = (C.c_int32 * E)()
+
+        def e2e_step():
+            rc = N.lib().qoa_b200_decode_all_batch(eng.handle, in_ptrs, in_lens, E, N.DECODE_ALL, out_ptrs, out_caps,
+                                                   None, stat)
+            assert rc == 0 and all(s == 0 for s in stat)
+
+        for _ in range(3):
+            e2e_step()
+        reps = max(3, min(K, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        e2e = {"value": E * out_per * world * reps / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": E * size,
+               "d2h_bytes_per_step": E * out_per * 2, "streams_per_gpu": E, "ms_per_step": dt / reps * 1e3,
+               "api": "qoa_b200_decode_all_batch (pinned host buffers -> H2D -> index + decode -> D2H)"}
+        if rank == 0:
+            assert torch.equal(h_out[:out_per], pcm[:out_per].cpu()), "e2e output differs from the device path"
+        del h_in, h_out
+    del pcm, qoa
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- encode (configs[3] shape, time-chunked) ----
+    encode = None
+    if not args.no_encode:
+        ES, F = args.enc_streams, args.enc_frames
+        chunk = F * 5120
+        epcm = torch.empty(ES * chunk * ENC_CH, dtype=torch.int16, device=dev)
+        fbytes = 8 + 16 * ENC_CH + 2048 * ENC_CH
+        eout = torch.empty(ES * F * fbytes, dtype=torch.uint8, device=dev)
+        batch = eng.encoder_batch([(ENC_CH, ENC_RATE, ENC_SAMPLES)] * ES)
+        p_off = np.arange(ES, dtype=np.uint64) * np.uint64(chunk * ENC_CH)
+        o_off = np.arange(ES, dtype=np.uint64) * np.uint64(F * fbytes)
+        cs = np.full(ES, chunk, dtype=np.uint32)
+        pos = 0
+        for _ in range(W):
+            eng.gen_pcm_dev(epcm.data_ptr(), ES, rank * ES, ENC_CH, chunk, pos, 1, "music", stream)
+            batch.encode_chunk_dev(epcm.data_ptr(), p_off, cs, eout.data_ptr(), o_off, stream)
+            pos += chunk
+        KE = max(3, min(K, 10))
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE)]
+        sampler2 = ClockSampler(local)
+        l0 = eng.kernel_launches()
+        barrier()
+        sampler2.start()
+        for k in range(KE):
+            eng.gen_pcm_dev(epcm.data_ptr(), ES, rank * ES, ENC_CH, chunk, pos, 1, "music", stream)  # untimed input prep
+            ev[k][0].record()
+            batch.encode_chunk_dev(epcm.data_ptr(), p_off, cs, eout.data_ptr(), o_off, stream)
+            ev[k][1].record()
+            pos += chunk
+        barrier()
+        clocks2 = sampler2.stop()
+        enc_ms = reduce_max(sum(a.elapsed_time(b) for a, b in ev))
+        enc_samples = ES * chunk * ENC_CH * world * KE
+        enc_value = enc_samples / (enc_ms * 1e-3) / 1e6
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        max_mhz = clocks2.get("sm_max_mhz") or 1965
+        nominal_peak = sm_count * 128 * max_mhz * 1e6
+        measured = {k: eng.int_issue_peak(i) for i, k in enumerate(("imad", "lop3", "mix"))}
+        per_gpu_ops = enc_value * 1e6 / world * ENC_OPS_PER_SAMPLE
+        encode = {"metric": "batch encode throughput", "value": enc_value, "unit": "Msamples/s",
+                  "ms_per_step": enc_ms / KE, "steps": KE, "gpu_launches": eng.kernel_launches() - l0,
+                  "config": {"workload": f"batch encode {ES} synthetic stereo 48 kHz streams per GPU (BASELINE.json "
+                                         f"configs[3] shape), time-chunked: {F} frames ({chunk} samples/ch) of every "
+                                         "stream per step, LMS state persistent on the device, PCM generated on device",
+                             "streams_per_gpu": ES, "frames_per_step": F},
+                  "roofline": {"bound": "int32-issue", "achieved": per_gpu_ops / 1e12,
+                               "peak": nominal_peak / 1e12, "unit": "Tops/s (944 algorithmic int-ops per sample)",
+                               "frac": per_gpu_ops / nominal_peak,
+                               "peak_kind": f"nominal {sm_count} SMs x 128 lanes x {max_mhz} MHz",
+                               "measured_issue_peaks_tops": {k: v / 1e12 for k, v in measured.items()},
+                               "frac_of_measured_mix_peak": per_gpu_ops / measured["mix"], "traffic": None},
+                  "clocks": clocks2}
+        batch.close()
+        del epcm, eout
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = cpu_enc = None
+    if not args.no_cpu:
+        cpu, cpu_enc = cpu_reference(args, want_encode=not args.no_encode)
+        if encode is not None:
+            encode["cpu_baseline"] = cpu_enc
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": "batch decode throughput", "value": dec_value, "unit": "Msamples/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": dec_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "i32", "data": "synthetic", "config": workload_config(args),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "decode_stereo_kernel", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "peak_kind": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "of fallback"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
+        "encode": encode,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,8 @@
 
 This is the host-side mirror of the reference's encoder/decoder objects for BATCHES of streams.  The per-stream,
 crate-shaped API (encode_all, QoaEncoder, QoaDecoder, ...) lives in api.py and is a thin layer over this module.
+Per-stream tables (offsets, lengths, capacities) may be python sequences or numpy arrays; numpy arrays of the right
+dtype are passed to the library without conversion (what bench.py uses for 8192-stream batches).
 """
 import ctypes as C
 import os
@@ -11,9 +13,30 @@ import numpy as np
 
 from . import _native as N
 
+_NP_OF = {C.c_uint64: np.uint64, C.c_size_t: np.uint64, C.c_uint32: np.uint32, C.c_int32: np.int32}
 
-def _arr(values, ctype):
-    return (ctype * len(values))(*values)
+INFO_DTYPE = np.dtype([("status", np.int32), ("streaming", np.int32), ("header_samples", np.uint32),
+                       ("channels", np.uint32), ("sample_rate", np.uint32), ("index_frames", np.uint32),
+                       ("samples", np.uint64), ("frames", np.uint64), ("max_channels", np.uint32),
+                       ("flags", np.uint32)])
+assert INFO_DTYPE.itemsize == C.sizeof(N.StreamInfo)
+
+
+class _Keep(list):
+    """Builds ctypes array arguments and keeps their backing storage alive for the duration of a call."""
+
+    def arr(self, values, ctype):
+        if isinstance(values, np.ndarray):
+            a = np.ascontiguousarray(values, dtype=_NP_OF[ctype])
+            self.append(a)
+            return C.cast(C.c_void_p(a.ctypes.data), C.POINTER(ctype))
+        a = (ctype * len(values))(*values)
+        self.append(a)
+        return a
+
+
+def _descs(descs):
+    return (N.Desc * len(descs))(*[N.Desc(int(c), int(r), int(s)) for (c, r, s) in descs])
 
 
 class Engine:
@@ -51,24 +74,23 @@ class Engine:
     # ---- encode, host buffers ------------------------------------------------------------------------------
     def encode_all_batch(self, pcm_list, descs):
         """Batched encode_all (src/lib.rs:760).  pcm_list[i]: int16 array (interleaved), descs[i]: (channels,
-        sample_rate, samples).  Returns (status list, list of bytes-like np.uint8 arrays)."""
+        sample_rate, samples).  Returns (status list, list of np.uint8 arrays)."""
         n = len(pcm_list)
         assert len(descs) == n
         if n == 0:
             return [], []
+        k = _Keep()
         pcm = [np.ascontiguousarray(p, dtype=np.int16).reshape(-1) for p in pcm_list]
-        d = (N.Desc * n)(*[N.Desc(int(c), int(r), int(s)) for (c, r, s) in descs])
         outs = []
         for (c, r, s) in descs:
             ok = 1 <= c <= 8 and r > 0 and s > 0
             outs.append(np.empty(N.lib().qoa_b200_encoded_size(c, s) if ok else 0, dtype=np.uint8))
-        pcm_ptr = _arr([p.ctypes.data if p.size else None for p in pcm], C.c_void_p)
-        pcm_len = _arr([p.size for p in pcm], C.c_size_t)
-        out_ptr = _arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p)
-        out_cap = _arr([o.size for o in outs], C.c_size_t)
         out_len = (C.c_size_t * n)()
         status = (C.c_int32 * n)()
-        rc = N.lib().qoa_b200_encode_all_batch(self._h, d, pcm_ptr, pcm_len, out_ptr, out_cap, out_len, status, n)
+        rc = N.lib().qoa_b200_encode_all_batch(
+            self._h, _descs(descs), k.arr([p.ctypes.data if p.size else None for p in pcm], C.c_void_p),
+            k.arr([p.size for p in pcm], C.c_size_t), k.arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p),
+            k.arr([o.size for o in outs], C.c_size_t), out_len, status, n)
         N.check(self._h, rc, "qoa_b200_encode_all_batch")
         return list(status), [o[:out_len[i]] for i, o in enumerate(outs)]
 
@@ -76,13 +98,13 @@ class Engine:
     def encode_all_batch_dev(self, descs, d_pcm, pcm_off, pcm_len, d_out, out_off, out_cap, stream=0):
         """Device-resident batched encode_all.  d_pcm/d_out: raw device pointers (int).  Returns (status, out_len)."""
         n = len(descs)
-        d = (N.Desc * n)(*[N.Desc(int(c), int(r), int(s)) for (c, r, s) in descs])
+        k = _Keep()
         out_len = (C.c_size_t * n)()
         status = (C.c_int32 * n)()
-        rc = N.lib().qoa_b200_encode_all_batch_dev(self._h, d, C.c_void_p(d_pcm), _arr(pcm_off, C.c_uint64),
-                                                   _arr(pcm_len, C.c_size_t), C.c_void_p(d_out),
-                                                   _arr(out_off, C.c_uint64), _arr(out_cap, C.c_size_t), out_len,
-                                                   status, n, C.c_void_p(stream))
+        rc = N.lib().qoa_b200_encode_all_batch_dev(
+            self._h, _descs(descs), C.c_void_p(d_pcm), k.arr(pcm_off, C.c_uint64), k.arr(pcm_len, C.c_size_t),
+            C.c_void_p(d_out), k.arr(out_off, C.c_uint64), k.arr(out_cap, C.c_size_t), out_len, status, n,
+            C.c_void_p(stream))
         N.check(self._h, rc, "qoa_b200_encode_all_batch_dev")
         return list(status), list(out_len)
 
@@ -130,10 +152,9 @@ class EncoderBatch:
         self.engine = engine
         self.descs = [(int(c), int(r), int(s)) for (c, r, s) in descs]
         n = len(self.descs)
-        d = (N.Desc * n)(*[N.Desc(c, r, s) for (c, r, s) in self.descs])
         st = (C.c_int32 * n)()
         self._h = C.c_void_p()
-        rc = N.lib().qoa_b200_encoder_batch_new(engine.handle, d, n, st, C.byref(self._h))
+        rc = N.lib().qoa_b200_encoder_batch_new(engine.handle, _descs(self.descs), n, st, C.byref(self._h))
         N.check(engine.handle, rc, "qoa_b200_encoder_batch_new")
         self.status = list(st)
 
@@ -151,43 +172,45 @@ class EncoderBatch:
     def write_header(self):
         n = len(self.descs)
         bufs = [np.zeros(8, dtype=np.uint8) for _ in range(n)]
-        rc = N.lib().qoa_b200_encoder_batch_write_header(self._h, _arr([b.ctypes.data for b in bufs], C.c_void_p))
+        k = _Keep()
+        rc = N.lib().qoa_b200_encoder_batch_write_header(self._h, k.arr([b.ctypes.data for b in bufs], C.c_void_p))
         N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_write_header")
         return [b.tobytes() for b in bufs]
 
     def encode_frame(self, pcm_list):
         """pcm_list[i]: int16 array for stream i's next frame, or None to skip the stream this round.
         Returns (status list, list of bytes)."""
-        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_frame, None)
+        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_frame, False)
 
     def encode_chunk(self, pcm_list):
         """Like encode_frame but any number of samples per stream (cut into frames of 5120)."""
-        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_chunk, "chunk")
+        return self._encode_host(pcm_list, N.lib().qoa_b200_encoder_batch_encode_chunk, True)
 
-    def _encode_host(self, pcm_list, fn, kind):
+    def _encode_host(self, pcm_list, fn, chunk):
         n = len(self.descs)
         assert len(pcm_list) == n
         pcm = [None if p is None else np.ascontiguousarray(p, dtype=np.int16).reshape(-1) for p in pcm_list]
-        if kind == "chunk":
-            caps = [0 if p is None or c == 0 else N.lib().qoa_b200_encoded_size(c, -(-p.size // c)) for p, (c, _, _) in
-                    zip(pcm, self.descs)]
+        if chunk:
+            caps = [8 if p is None or c == 0 else N.lib().qoa_b200_encoded_size(c, -(-p.size // c))
+                    for p, (c, _, _) in zip(pcm, self.descs)]
         else:
             caps = [8 + 16 * 8 + 8 * 256 * 8] * n
-        outs = [np.empty(max(c, 8), dtype=np.uint8) for c in caps]
+        outs = [np.empty(c, dtype=np.uint8) for c in caps]
         written = (C.c_size_t * n)()
         status = (C.c_int32 * n)()
         dummy = np.zeros(1, dtype=np.int16)  # a non-NULL pointer for "fed an empty frame" (-> InvalidSamples)
         ptrs = [None if p is None else (p.ctypes.data if p.size else dummy.ctypes.data) for p in pcm]
-        rc = fn(self._h, _arr(ptrs, C.c_void_p), _arr([0 if p is None else p.size for p in pcm], C.c_size_t),
-                _arr([o.ctypes.data for o in outs], C.c_void_p), _arr([o.size for o in outs], C.c_size_t), written,
-                status)
+        k = _Keep()
+        rc = fn(self._h, k.arr(ptrs, C.c_void_p), k.arr([0 if p is None else p.size for p in pcm], C.c_size_t),
+                k.arr([o.ctypes.data for o in outs], C.c_void_p), k.arr(caps, C.c_size_t), written, status)
         N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_encode_frame/chunk")
         return list(status), [outs[i][:written[i]].tobytes() for i in range(n)]
 
     def encode_chunk_dev(self, d_pcm, pcm_off, chunk_samples, d_out, out_off, stream=0):
+        k = _Keep()
         rc = N.lib().qoa_b200_encoder_batch_encode_chunk_dev(
-            self._h, C.c_void_p(d_pcm), _arr(pcm_off, C.c_uint64), _arr(chunk_samples, C.c_uint32), C.c_void_p(d_out),
-            _arr(out_off, C.c_uint64), C.c_void_p(stream))
+            self._h, C.c_void_p(d_pcm), k.arr(pcm_off, C.c_uint64), k.arr(chunk_samples, C.c_uint32),
+            C.c_void_p(d_out), k.arr(out_off, C.c_uint64), C.c_void_p(stream))
         N.check(self.engine.handle, rc, "qoa_b200_encoder_batch_encode_chunk_dev")
 
     def lms(self, i, c):
@@ -205,16 +228,23 @@ class DecodePlan:
         self._h = C.c_void_p()
         self.engine = None
         self.n = 0
-        self.info = []
+        self.info_array = np.zeros(0, dtype=INFO_DTYPE)
+        self._info = None
         self._keep = None
 
-    @staticmethod
-    def _info_list(h, n):
-        arr = (N.StreamInfo * max(n, 1))()
-        N.lib().qoa_b200_decode_plan_info(h, arr)
-        return [dict(status=a.status, streaming=bool(a.streaming), header_samples=a.header_samples, channels=a.channels,
-                     sample_rate=a.sample_rate, samples=int(a.samples), frames=int(a.frames),
-                     index_frames=a.index_frames, max_channels=a.max_channels, flags=a.flags) for a in arr[:n]]
+    def _load_info(self):
+        self.info_array = np.zeros(self.n, dtype=INFO_DTYPE)
+        if self.n:
+            N.lib().qoa_b200_decode_plan_info(self._h, C.c_void_p(self.info_array.ctypes.data))
+
+    @property
+    def info(self):
+        """Per-stream dicts (status, streaming, header_samples, channels, sample_rate, samples, frames, ...)."""
+        if self._info is None:
+            names = INFO_DTYPE.names
+            self._info = [{k: (bool(row[k]) if k == "streaming" else int(row[k])) for k in names}
+                          for row in self.info_array]
+        return self._info
 
     @classmethod
     def _from_host(cls, engine, streams, mode):
@@ -225,11 +255,12 @@ class DecodePlan:
         n = len(bufs)
         self.n = n
         self._keep = bufs
+        k = _Keep()
         rc = N.lib().qoa_b200_decode_plan_create(
-            engine.handle, _arr([b.ctypes.data if b.size else None for b in bufs], C.c_void_p),
-            _arr([b.size for b in bufs], C.c_size_t), n, mode, C.byref(self._h))
+            engine.handle, k.arr([b.ctypes.data if b.size else None for b in bufs], C.c_void_p),
+            k.arr([b.size for b in bufs], C.c_size_t), n, mode, C.byref(self._h))
         N.check(engine.handle, rc, "qoa_b200_decode_plan_create")
-        self.info = cls._info_list(self._h, n)
+        self._load_info()
         return self
 
     @classmethod
@@ -238,11 +269,12 @@ class DecodePlan:
         self.engine = engine
         n = len(lens)
         self.n = n
-        rc = N.lib().qoa_b200_decode_plan_create_dev(engine.handle, C.c_void_p(d_qoa), _arr(in_off, C.c_uint64),
-                                                     _arr(lens, C.c_size_t), n, mode, C.c_void_p(stream),
+        k = _Keep()
+        rc = N.lib().qoa_b200_decode_plan_create_dev(engine.handle, C.c_void_p(d_qoa), k.arr(in_off, C.c_uint64),
+                                                     k.arr(lens, C.c_size_t), n, mode, C.c_void_p(stream),
                                                      C.byref(self._h))
         N.check(engine.handle, rc, "qoa_b200_decode_plan_create_dev")
-        self.info = cls._info_list(self._h, n)
+        self._load_info()
         return self
 
     def close(self):
@@ -257,7 +289,7 @@ class DecodePlan:
             pass
 
     def frame_headers(self, i):
-        cnt = self.info[i]["index_frames"]
+        cnt = int(self.info_array["index_frames"][i])
         arr = (N.FrameHeaderC * max(cnt, 1))()
         got = N.lib().qoa_b200_decode_plan_frame_headers(self._h, i, arr, cnt)
         return [(a.num_channels, a.sample_rate, a.num_samples_per_channel) for a in arr[:min(got, cnt)]]
@@ -267,24 +299,29 @@ class DecodePlan:
         n = self.n
         if n == 0:
             return []
+        counts = [int(v) for v in self.info_array["samples"]]
         if caps is None:
-            caps = [inf["samples"] for inf in self.info]
+            caps = counts
         outs = [np.empty(c, dtype=np.int16) for c in caps]
         status = (C.c_int32 * n)()
-        rc = N.lib().qoa_b200_decode_plan_run(self._h, _arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p),
-                                              _arr(caps, C.c_size_t), status)
+        k = _Keep()
+        rc = N.lib().qoa_b200_decode_plan_run(self._h, k.arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p),
+                                              k.arr(caps, C.c_size_t), status)
         N.check(self.engine.handle, rc, "qoa_b200_decode_plan_run")
         self.run_status = list(status)
-        return [o[:min(self.info[i]["samples"], caps[i])] if status[i] != N.DEC_OUTPUT_TOO_SMALL else o[:0]
+        return [o[:min(counts[i], caps[i])] if status[i] != N.DEC_OUTPUT_TOO_SMALL else o[:0]
                 for i, o in enumerate(outs)]
 
     def run_dev(self, d_out, out_off, out_cap, stream=0):
+        """Decode into a device arena; returns the per-stream status as an np.int32 array."""
         n = self.n
-        status = (C.c_int32 * max(n, 1))()
-        rc = N.lib().qoa_b200_decode_plan_run_dev(self._h, C.c_void_p(d_out), _arr(out_off, C.c_uint64),
-                                                  _arr(out_cap, C.c_size_t), status, C.c_void_p(stream))
+        status = np.zeros(n, dtype=np.int32)
+        k = _Keep()
+        rc = N.lib().qoa_b200_decode_plan_run_dev(self._h, C.c_void_p(d_out), k.arr(out_off, C.c_uint64),
+                                                  k.arr(out_cap, C.c_size_t), C.c_void_p(status.ctypes.data),
+                                                  C.c_void_p(stream))
         N.check(self.engine.handle, rc, "qoa_b200_decode_plan_run_dev")
-        return list(status[:n])
+        return status
 
 
 _default = None

@@ -329,7 +329,7 @@ def test_gen_qoa_decodes_like_oracle(eng):
     out = torch.zeros(3 * n * ch, dtype=torch.int16, device="cuda")
     st = plan.run_dev(out.data_ptr(), [i * n * ch for i in range(3)], [n * ch] * 3)
     torch.cuda.synchronize()
-    assert st == [0, 0, 0]
+    assert list(st) == [0, 0, 0]
     got = out.cpu().numpy().reshape(3, -1)
     for i in range(3):
         assert np.array_equal(got[i], ob.decode_all(streams[i])[1])
