@@ -331,16 +331,52 @@ struct SingleLoop<20> {
     static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, int16_t *) {}
 };
 
-// ---- stereo fast path: one thread = one frame (both channels, two independent LMS chains = ILP 2) -------------
-// Requirements (checked by the host from the index flags): every frame has 2 channels and starts 16-byte aligned
-// in the PCM output.
-__global__ void __launch_bounds__(kDecThreads)
+// ---- stereo fast path ------------------------------------------------------------------------------------------
+// One thread = one frame, both channels (two independent LMS chains = ILP 2; (L, R) pairs pack into one 32-bit word).
+// Requirements (checked by the host from the index flags): every frame has 2 channels and starts 16-byte aligned in
+// the PCM output.
+//
+// Memory path.  Lanes of a warp own different frames (4136 B apart in the input, 20480 B apart in the output), so
+// direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages kGroup
+// slices (kGroup * 80 B of interleaved PCM) in its own shared-memory row and hands the row to the TMA engine as one
+// bulk copy (cp.async.bulk shared -> global): zero copy-out instructions, full-sector writes, and no barrier of any
+// kind because a row is private to its lane.  Rows are double-buffered; the row pitch (S*80 + 16 bytes) is an odd
+// multiple of 16 so that the 128-bit staging stores of a quarter-warp hit eight distinct bank groups.
+// Slice words are fetched as 16-byte aligned vectors one group ahead of use (frames are only 8-byte aligned).
+template <int S>
+struct StereoCfg {
+    static constexpr int kRowBytes = S * 80;        // PCM bytes one lane produces per group
+    static constexpr int kPitch = kRowBytes + 16;   // odd multiple of 16 bytes
+    static constexpr int kVec = S + 1;              // aligned 16-byte vectors covering S slices (2 x u64 each) at any 8-byte skew
+};
+
+__device__ __forceinline__ void bulk_store_s2g(void *gptr, uint32_t saddr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(saddr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int S, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                      const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
 {
-    __shared__ DecLut lut;
+    using Cfg = StereoCfg<S>;
+    extern __shared__ __align__(16384) uint8_t smem[];
+    DecLut &lut = *reinterpret_cast<DecLut *>(smem);
     fill_lut(lut);
-    const uint64_t fi = (uint64_t)blockIdx.x * kDecThreads + threadIdx.x;
+    const uint64_t fi = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     if (fi >= n_frames) return;
     const FrameRec rec = recs[fi];
     const uint64_t ob = out_base[rec.stream];
@@ -351,35 +387,67 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
     Chain a, b;
     load_lms(a, fp + 8);
     load_lms(b, fp + 24);
-    const uint8_t *sp = fp + 40;
-    const uint32_t nfull = nsamp / kSliceLen;
-    uint32_t *op = reinterpret_cast<uint32_t *>(out + ob + rec.out_rel);
+    const uint8_t *sp = fp + 40;                                    // first slice word (8-byte aligned)
+    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 8);
+    const uint4 *vp = reinterpret_cast<const uint4 *>(sp - skew);    // 16-byte aligned superset
+    const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
+    const uint32_t nvec = (skew + nslices * 16 + 15) / 16;          // vectors that hold any byte of this frame's slices
+    const uint32_t ngroups = (nslices + S - 1) / S;
+    uint8_t *op = reinterpret_cast<uint8_t *>(out + ob + rec.out_rel);
     const uint32_t lane_row = smem_u32(&lut.v[0]) + (threadIdx.x & 31) * 4;
+    const uint32_t stage = smem_u32(smem + sizeof(DecLut)) + threadIdx.x * (2 * Cfg::kPitch);
+    if (lane_row & 0x380u) __trap(); // the LUT must be 1 KiB aligned in the shared window (code offsets are OR-ed in)
 
-    for (uint32_t k = 0; k < nfull; ++k) {
-        const uint2 wa = ldg_be64(sp + (uint64_t)k * 16);
-        const uint2 wb = ldg_be64(sp + (uint64_t)k * 16 + 8);
-        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
-        const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
-        uint32_t o[20];
-        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-        uint4 *dst = reinterpret_cast<uint4 *>(op + (uint64_t)k * kSliceLen);
+    uint4 cur[Cfg::kVec], nxt[Cfg::kVec];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-    }
-    const uint32_t rem = nsamp - nfull * kSliceLen; // partial last slice: decoded in full, `rem` samples emitted (:320-325)
-    if (rem) {
-        const uint2 wa = ldg_be64(sp + (uint64_t)nfull * 16);
-        const uint2 wb = ldg_be64(sp + (uint64_t)nfull * 16 + 8);
-        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
-        const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
-        uint32_t o[20];
-        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-        uint32_t *dst = op + (uint64_t)nfull * kSliceLen;
+    for (int v = 0; v < Cfg::kVec; ++v) cur[v] = (uint32_t)v < nvec ? __ldg(vp + v) : make_uint4(0, 0, 0, 0);
+
+    for (uint32_t g = 0; g < ngroups; ++g) {
+        // prefetch the next group's slice words (vector S of this group == vector 0 of the next one)
 #pragma unroll
-        for (int i = 0; i < 20; ++i)
-            if ((uint32_t)i < rem) dst[i] = o[i];
+        for (int v = 0; v < Cfg::kVec; ++v) {
+            const uint32_t j = (g + 1) * S + v;
+            nxt[v] = j < nvec ? __ldg(vp + j) : make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t row = stage + (g & 1) * Cfg::kPitch;
+        bulk_wait_read<1>(); // the bulk copy that last read this row (two groups ago) has drained it
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            // slice s of the group = bytes [skew + 16 s, skew + 16 s + 16) of cur[]
+            uint32_t a_hi, a_lo, b_hi, b_lo;
+            if (skew) {
+                a_hi = cur[s].z; a_lo = cur[s].w; b_hi = cur[s + 1].x; b_lo = cur[s + 1].y;
+            } else {
+                a_hi = cur[s].x; a_lo = cur[s].y; b_hi = cur[s].z; b_lo = cur[s].w;
+            }
+            const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
+            const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+            uint32_t o[20];
+            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sts128(row + s * 80 + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        // hand the row to the TMA engine.  Samples past nsamp (partial last slice, :320-325) are not emitted.
+        const uint32_t first = g * (S * kSliceLen);
+        const uint32_t bytes = min((uint32_t)(S * kSliceLen), nsamp - first) * 4;
+        const uint32_t bulk = bytes & ~15u;
+        uint8_t *dst = op + (uint64_t)first * 4;
+        fence_async_smem();
+        if (bulk) bulk_store_s2g(dst, row, bulk);
+        bulk_commit();
+        if (bytes != bulk) { // 1..3 trailing (L, R) words of a frame whose sample count is not a multiple of 4
+            for (uint32_t t = bulk; t < bytes; t += 4) {
+                uint32_t v;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
+                *reinterpret_cast<uint32_t *>(dst + t) = v;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < Cfg::kVec; ++v) cur[v] = nxt[v];
     }
+    bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read every row
 }
 
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
@@ -426,9 +494,19 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
 {
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
     if (all_stereo) {
-        const uint64_t blocks = (n_frames + kDecThreads - 1) / kDecThreads;
+        constexpr int S = 4, THREADS = 256;
+        const size_t smem = sizeof(DecLut) + (size_t)THREADS * 2 * StereoCfg<S>::kPitch;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(decode_stereo_kernel<S, THREADS>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        decode_stereo_kernel<<<(unsigned)blocks, kDecThreads, 0, s>>>(d_arena, d_recs, n_frames, d_out_base, d_out);
+        decode_stereo_kernel<S, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
+                                                                                 d_out);
     } else {
         const uint64_t n_units = n_frames * max_ch;
         const uint64_t blocks = (n_units + kDecThreads - 1) / kDecThreads;
