@@ -8,6 +8,8 @@
 //   decode_all                            :713-747   extra IncompatibleFrame check
 // Every frame header carries its own LMS state (:270-281), so frames decode independently: one thread owns one
 // (frame, channel pair) and walks its slices; nothing crosses a frame.
+#include <cstdlib>
+
 #include "qoa_kernels.h"
 
 namespace qoa {
@@ -208,17 +210,19 @@ cudaError_t launch_index_fill(const uint8_t *d_arena, const uint64_t *d_in_off, 
 // Decode
 // ================================================================================================================
 
-constexpr int kDecThreads = 128;
+// Dequant LUT in shared memory: entry (sf*8 + code) holds {dequantized, dequantized >> 4} (the residual and the LMS
+// delta of update(), src/lib.rs:822) and is replicated per lane so that every lane reads its own bank pair:
+// lane L's copy of entry e lives at byte e*256 + L*8 (32 KiB; an LDS.64 per half-warp is conflict-free).
+constexpr int kLutBytes = 128 * 32 * 8;
+constexpr uint32_t kLutAlign = 2048; // bits 8..10 of the base must be zero: code offsets are OR-ed into the address
 
-// Dequant LUT in shared memory, replicated per lane so that every lane reads its own bank:
-// entry (sf*8 + code) of lane L lives at byte ((sf*8 + code) * 32 + L) * 4  (16 KiB, conflict-free).
-struct __align__(16384) DecLut {
-    int v[128 * 32];
-};
-
-__device__ __forceinline__ void fill_lut(DecLut &lut)
+__device__ __forceinline__ void fill_lut(uint8_t *lut)
 {
-    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) lut.v[i] = c_dequant[i >> 5];
+    int2 *v = reinterpret_cast<int2 *>(lut);
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+        const int dq = c_dequant[i >> 5];
+        v[i] = make_int2(dq, dq >> 4);
+    }
     __syncthreads();
 }
 
@@ -251,13 +255,13 @@ __device__ __forceinline__ void load_lms(Chain &c, const uint8_t *p)
     c.s3 = sign_pm1(c.h3);
 }
 
-// Byte offset (code * 128) of sample I's 3-bit code inside the lane-replicated LUT row.
+// Byte offset (code * 256) of sample I's 3-bit code inside the lane-replicated LUT.
 // Slice word layout (:303, :308): sf in bits 63..60, sample i's code in bits 59-3i .. 57-3i.
 template <int I>
 __device__ __forceinline__ uint32_t code_off(uint32_t hi, uint32_t lo)
 {
     constexpr int pos = 57 - 3 * I; // LSB of the code within the 64-bit word
-    constexpr int sh = pos - 7;     // shift that brings the code to bits 9..7
+    constexpr int sh = pos - 8;     // shift that brings the code to bits 10..8
     uint32_t v;
     if constexpr (sh >= 32)
         v = hi >> (sh - 32);
@@ -267,29 +271,28 @@ __device__ __forceinline__ uint32_t code_off(uint32_t hi, uint32_t lo)
         v = lo;
     else
         v = lo << (-sh);
-    return v & 0x380u;
+    return v & 0x700u;
 }
 
-__device__ __forceinline__ int lds_s32(uint32_t addr)
+__device__ __forceinline__ int2 lds_v2(uint32_t addr)
 {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
 
-// One sample of one channel (:306-317).  `row` = shared address of the lane's LUT row for this slice's scalefactor
-// (1 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
+// One sample of one channel (:306-317).  `row` = shared address of the lane's LUT entries for this slice's
+// scalefactor (2 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
 template <int I>
 __device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
 {
-    const int dq = lds_s32(row | code_off<I>(hi, lo));
+    const int2 t = lds_v2(row | code_off<I>(hi, lo));                             // {dequantized, delta}
     const int p = (c.w0 * c.h0 + c.w1 * c.h1 + c.w2 * c.h2 + c.w3 * c.h3) >> 13; // predict :799-805
-    const int r = clamp_i16(p + dq);                                              // :310
-    const int d = dq >> 4;                                                        // update :822
-    c.w0 += c.s0 * d;
-    c.w1 += c.s1 * d;
-    c.w2 += c.s2 * d;
-    c.w3 += c.s3 * d;
+    const int r = clamp_i16(p + t.x);                                             // :310
+    c.w0 += c.s0 * t.y;                                                           // update :821-828
+    c.w1 += c.s1 * t.y;
+    c.w2 += c.s2 * t.y;
+    c.w3 += c.s3 * t.y;
     c.h0 = c.h1;
     c.h1 = c.h2;
     c.h2 = c.h3;
@@ -337,17 +340,19 @@ struct SingleLoop<20> {
 // the PCM output.
 //
 // Memory path.  Lanes of a warp own different frames (4136 B apart in the input, 20480 B apart in the output), so
-// direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages kGroup
-// slices (kGroup * 80 B of interleaved PCM) in its own shared-memory row and hands the row to the TMA engine as one
-// bulk copy (cp.async.bulk shared -> global): zero copy-out instructions, full-sector writes, and no barrier of any
-// kind because a row is private to its lane.  Rows are double-buffered; the row pitch (S*80 + 16 bytes) is an odd
+// direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages S slices
+// (S * 80 B of interleaved PCM) in its own shared-memory row and hands the row to the TMA engine as one bulk copy
+// (cp.async.bulk shared -> global): zero copy-out instructions, full-sector writes, and no barrier of any kind
+// because a row is private to its lane.  NB rows per lane form a ring; the row pitch (S*80 + 16 bytes) is an odd
 // multiple of 16 so that the 128-bit staging stores of a quarter-warp hit eight distinct bank groups.
-// Slice words are fetched as 16-byte aligned vectors one group ahead of use (frames are only 8-byte aligned).
-template <int S>
+// Slice words are fetched as 16-byte aligned vectors two slices ahead of use (frames are only 8-byte aligned: a
+// slice pair is either one vector or the upper half of one and the lower half of the next).
+template <int S, int NB>
 struct StereoCfg {
-    static constexpr int kRowBytes = S * 80;        // PCM bytes one lane produces per group
-    static constexpr int kPitch = kRowBytes + 16;   // odd multiple of 16 bytes
-    static constexpr int kVec = S + 1;              // aligned 16-byte vectors covering S slices (2 x u64 each) at any 8-byte skew
+    static constexpr int kRowBytes = S * 80;                                  // PCM bytes one lane produces per group
+    static constexpr int kPitch = (S % 2 == 0) ? kRowBytes + 16 : kRowBytes + 32; // odd multiple of 16 bytes
+    static constexpr int kLaneBytes = NB * kPitch;
+    static_assert((kPitch / 16) % 2 == 1, "row pitch must be an odd multiple of 16 bytes");
 };
 
 __device__ __forceinline__ void bulk_store_s2g(void *gptr, uint32_t saddr, uint32_t bytes)
@@ -367,15 +372,16 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int S, int THREADS>
+template <int S, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                      const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
 {
-    using Cfg = StereoCfg<S>;
-    extern __shared__ __align__(16384) uint8_t smem[];
-    DecLut &lut = *reinterpret_cast<DecLut *>(smem);
-    fill_lut(lut);
+    using Cfg = StereoCfg<S, NB>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
+    uint8_t *smem = smem_raw + pad;
+    fill_lut(smem);
     const uint64_t fi = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
     if (fi >= n_frames) return;
     const FrameRec rec = recs[fi];
@@ -392,72 +398,76 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
     const uint4 *vp = reinterpret_cast<const uint4 *>(sp - skew);    // 16-byte aligned superset
     const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
     const uint32_t nvec = (skew + nslices * 16 + 15) / 16;          // vectors that hold any byte of this frame's slices
-    const uint32_t ngroups = (nslices + S - 1) / S;
     uint8_t *op = reinterpret_cast<uint8_t *>(out + ob + rec.out_rel);
-    const uint32_t lane_row = smem_u32(&lut.v[0]) + (threadIdx.x & 31) * 4;
-    const uint32_t stage = smem_u32(smem + sizeof(DecLut)) + threadIdx.x * (2 * Cfg::kPitch);
-    if (lane_row & 0x380u) __trap(); // the LUT must be 1 KiB aligned in the shared window (code offsets are OR-ed in)
+    const uint32_t lane_row = smem_u32(smem) + (threadIdx.x & 31) * 8;
+    const uint32_t stage = smem_u32(smem + kLutBytes) + threadIdx.x * Cfg::kLaneBytes;
 
-    uint4 cur[Cfg::kVec], nxt[Cfg::kVec];
-#pragma unroll
-    for (int v = 0; v < Cfg::kVec; ++v) cur[v] = (uint32_t)v < nvec ? __ldg(vp + v) : make_uint4(0, 0, 0, 0);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 v0 = __ldg(vp);                       // vector holding the first half of the current slice pair
+    uint4 v1 = 1 < nvec ? __ldg(vp + 1) : zero; // the one after it
+    uint4 v2 = 2 < nvec ? __ldg(vp + 2) : zero; // prefetched
+    uint32_t ring = 0;                           // row of the ring being filled
+    uint32_t in_row = 0;                         // slices already staged in it
+    uint32_t first = 0;                          // per-channel sample index of the row's first sample
 
-    for (uint32_t g = 0; g < ngroups; ++g) {
-        // prefetch the next group's slice words (vector S of this group == vector 0 of the next one)
-#pragma unroll
-        for (int v = 0; v < Cfg::kVec; ++v) {
-            const uint32_t j = (g + 1) * S + v;
-            nxt[v] = j < nvec ? __ldg(vp + j) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (uint32_t k = 0; k < nslices; ++k) {
+        uint32_t a_hi, a_lo, b_hi, b_lo;
+        if (skew) {
+            a_hi = v0.z; a_lo = v0.w; b_hi = v1.x; b_lo = v1.y;
+        } else {
+            a_hi = v0.x; a_lo = v0.y; b_hi = v0.z; b_lo = v0.w;
         }
-        const uint32_t row = stage + (g & 1) * Cfg::kPitch;
-        bulk_wait_read<1>(); // the bulk copy that last read this row (two groups ago) has drained it
+        v0 = v1;
+        v1 = v2;
+        v2 = k + 3 < nvec ? __ldg(vp + k + 3) : zero;
+        const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
+        const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 2048; // sf = top nibble (:303)
+        const uint32_t row_b = lane_row + (wb.x >> 28) * 2048;
+        const uint32_t row = stage + ring * Cfg::kPitch;
+        if (in_row == 0) bulk_wait_read<NB - 1>(); // the bulk copy that last read this row has drained it
+        uint32_t o[20];
+        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+        const uint32_t dst_s = row + in_row * 80;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            // slice s of the group = bytes [skew + 16 s, skew + 16 s + 16) of cur[]
-            uint32_t a_hi, a_lo, b_hi, b_lo;
-            if (skew) {
-                a_hi = cur[s].z; a_lo = cur[s].w; b_hi = cur[s + 1].x; b_lo = cur[s + 1].y;
-            } else {
-                a_hi = cur[s].x; a_lo = cur[s].y; b_hi = cur[s].z; b_lo = cur[s].w;
+        for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        ++in_row;
+        if (in_row == S || k + 1 == nslices) {
+            // hand the row to the TMA engine.  Samples past nsamp (partial last slice, :320-325) are not emitted.
+            const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * 4;
+            const uint32_t bulk = bytes & ~15u;
+            uint8_t *dst = op + (uint64_t)first * 4;
+            fence_async_smem();
+            if (bulk) bulk_store_s2g(dst, row, bulk);
+            bulk_commit();
+            if (bytes != bulk) { // 1..3 trailing (L, R) words of a frame whose sample count is not a multiple of 4
+                for (uint32_t t = bulk; t < bytes; t += 4) {
+                    uint32_t v;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
+                    *reinterpret_cast<uint32_t *>(dst + t) = v;
+                }
             }
-            const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
-            const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
-            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
-            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
-            uint32_t o[20];
-            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) sts128(row + s * 80 + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            first += in_row * kSliceLen;
+            in_row = 0;
+            ring = (ring + 1 == NB) ? 0 : ring + 1;
         }
-        // hand the row to the TMA engine.  Samples past nsamp (partial last slice, :320-325) are not emitted.
-        const uint32_t first = g * (S * kSliceLen);
-        const uint32_t bytes = min((uint32_t)(S * kSliceLen), nsamp - first) * 4;
-        const uint32_t bulk = bytes & ~15u;
-        uint8_t *dst = op + (uint64_t)first * 4;
-        fence_async_smem();
-        if (bulk) bulk_store_s2g(dst, row, bulk);
-        bulk_commit();
-        if (bytes != bulk) { // 1..3 trailing (L, R) words of a frame whose sample count is not a multiple of 4
-            for (uint32_t t = bulk; t < bytes; t += 4) {
-                uint32_t v;
-                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
-                *reinterpret_cast<uint32_t *>(dst + t) = v;
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < Cfg::kVec; ++v) cur[v] = nxt[v];
     }
     bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read every row
 }
 
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
-__global__ void __launch_bounds__(kDecThreads)
+constexpr int kGenThreads = 128;
+
+__global__ void __launch_bounds__(kGenThreads)
 decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_units,
                       uint32_t max_ch, const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
 {
-    __shared__ DecLut lut;
+    // static shared memory starts at window offset 0x400 and __align__ is relative to that: align by hand
+    __shared__ __align__(16) uint8_t lut_raw[kLutBytes + kLutAlign];
+    uint8_t *lut = lut_raw + ((kLutAlign - (smem_u32(lut_raw) & (kLutAlign - 1))) & (kLutAlign - 1));
     fill_lut(lut);
-    const uint64_t u = (uint64_t)blockIdx.x * kDecThreads + threadIdx.x;
+    const uint64_t u = (uint64_t)blockIdx.x * kGenThreads + threadIdx.x;
     if (u >= n_units) return;
     const uint64_t fi = u / max_ch;
     const uint32_t c = (uint32_t)(u - fi * max_ch);
@@ -474,11 +484,11 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     const uint8_t *sp = fp + 8 + 16 * ch + 8 * c;
     const uint32_t ngroups = (nsamp + kSliceLen - 1) / kSliceLen;
     int16_t *op = out + ob + rec.out_rel + c;
-    const uint32_t lane_row = smem_u32(&lut.v[0]) + (threadIdx.x & 31) * 4;
+    const uint32_t lane_row = smem_u32(lut) + (threadIdx.x & 31) * 8;
 
     for (uint32_t k = 0; k < ngroups; ++k) {
         const uint2 wa = ldg_be64(sp + (uint64_t)k * ch * 8);
-        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 2048;
         int16_t o[20];
         SingleLoop<0>::run(a, row_a, wa, o);
         const uint32_t base = k * kSliceLen;
@@ -489,33 +499,54 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     }
 }
 
+template <int S, int NB, int THREADS>
+static cudaError_t launch_stereo(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
+                                 const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s)
+{
+    const size_t smem = kLutAlign + kLutBytes + (size_t)THREADS * StereoCfg<S, NB>::kLaneBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(decode_stereo_kernel<S, NB, THREADS>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    decode_stereo_kernel<S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
+                                                                                 d_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
                           bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s, int *n_launches)
 {
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
+    cudaError_t e;
     if (all_stereo) {
-        constexpr int S = 4, THREADS = 256;
-        const size_t smem = sizeof(DecLut) + (size_t)THREADS * 2 * StereoCfg<S>::kPitch;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(decode_stereo_kernel<S, THREADS>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            configured = true;
+        // QOA_B200_DEC_VARIANT selects a tuning variant (development aid; the default is the measured best).
+        static int variant = -1;
+        if (variant < 0) {
+            const char *v = getenv("QOA_B200_DEC_VARIANT");
+            variant = v ? atoi(v) : 0;
         }
-        const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
-        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        decode_stereo_kernel<S, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
-                                                                                 d_out);
+        switch (variant) {
+        case 1: e = launch_stereo<4, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        case 2: e = launch_stereo<4, 2, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        case 3: e = launch_stereo<3, 2, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        case 4: e = launch_stereo<2, 2, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        case 5: e = launch_stereo<8, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        default: e = launch_stereo<2, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        }
     } else {
         const uint64_t n_units = n_frames * max_ch;
-        const uint64_t blocks = (n_units + kDecThreads - 1) / kDecThreads;
+        const uint64_t blocks = (n_units + kGenThreads - 1) / kGenThreads;
         if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        decode_generic_kernel<<<(unsigned)blocks, kDecThreads, 0, s>>>(d_arena, d_recs, n_units, max_ch, d_out_base,
-                                                                       d_out);
+        decode_generic_kernel<<<(unsigned)blocks, kGenThreads, 0, s>>>(d_arena, d_recs, n_units, max_ch, d_out_base, d_out);
+        e = cudaGetLastError();
     }
     if (n_launches) *n_launches += 1;
-    return cudaGetLastError();
+    return e;
 }
 
 } // namespace qoa
