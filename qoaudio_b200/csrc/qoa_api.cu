@@ -731,6 +731,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     Scratch sc(ctx);
     std::vector<uint64_t> base(n);
     bool aligned = true;
+    uint64_t out_bytes = 0;
     for (size_t i = 0; i < n; ++i) {
         int st = plan->info[i].status;
         if (plan->info[i].samples > out_cap[i]) {
@@ -739,6 +740,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
         } else {
             base[i] = out_off[i];
             if (out_off[i] & 7) aligned = false;
+            out_bytes = std::max<uint64_t>(out_bytes, (out_off[i] + plan->info[i].samples) * 2);
         }
         if (status) status[i] = st;
     }
@@ -751,7 +753,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_base, base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     int nl = 0;
     CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs, plan->n_frames, plan->max_ch, plan->all_stereo && aligned,
-                                  d_base, d_out, s, &nl));
+                                  d_base, d_out, out_bytes, s, &nl));
     ctx->launches += nl;
     return 0;
 }

@@ -8,7 +8,10 @@
 //   decode_all                            :713-747   extra IncompatibleFrame check
 // Every frame header carries its own LMS state (:270-281), so frames decode independently: one thread owns one
 // (frame, channel pair) and walks its slices; nothing crosses a frame.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "qoa_kernels.h"
 
@@ -341,23 +344,42 @@ struct SingleLoop<20> {
 //
 // Memory path.  Lanes of a warp own different frames (4136 B apart in the input, 20480 B apart in the output), so
 // direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages S slices
-// (S * 80 B of interleaved PCM) in its own shared-memory row and hands the row to the TMA engine as one bulk copy
-// (cp.async.bulk shared -> global): zero copy-out instructions, full-sector writes, and no barrier of any kind
-// because a row is private to its lane.  NB rows per lane form a ring; the row pitch (S*80 + 16 bytes) is an odd
-// multiple of 16 so that the 128-bit staging stores of a quarter-warp hit eight distinct bank groups.
-// Slice words are fetched as 16-byte aligned vectors two slices ahead of use (frames are only 8-byte aligned: a
-// slice pair is either one vector or the upper half of one and the lower half of the next).
+// (S * 80 B of interleaved PCM) in its own row of a per-warp shared-memory tile [32 lanes][S * 80 B] and the tile goes
+// to global memory through the TMA engine:
+//   * regular warps (32 consecutive full frames of one stream, i.e. rows exactly 20480 B apart in the output): ONE
+//     2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = S*20 words x 32 rows of a tensor map that
+//     views the output arena as rows of 20480 bytes) — no copy-out instructions at all;
+//   * everything else (warps that straddle two streams, short last frames, partial slices, the group that crosses a
+//     20480-byte row of the arena-wide map): one 1-D bulk copy per lane (cp.async.bulk; the hardware takes uniform
+//     operands, so this path serialises over the lanes — it is the fallback, not the steady state).
+// S is odd so that the row pitch (S*80 bytes) is an odd multiple of 16: the 128-bit staging stores of a quarter-warp
+// then hit eight distinct bank groups.  NB tiles per warp form a ring.
+// Slice words arrive through a per-lane ring of four 16-byte vectors filled by cp.async two to three slices ahead
+// of use (frames are only 8-byte aligned: a slice pair is either one aligned vector or the upper half of one and the
+// lower half of the next — reading the ring with two 8-byte shared loads needs no alignment selects, and unlike a
+// register prefetch the asynchronous copy never shares a scoreboard slot with the LUT loads).
+constexpr uint32_t kOutRowBytes = kFrameLen * 2 * 2; // PCM bytes of one full stereo frame = row pitch of the tensor map
+
 template <int S, int NB>
 struct StereoCfg {
-    static constexpr int kRowBytes = S * 80;                                  // PCM bytes one lane produces per group
-    static constexpr int kPitch = (S % 2 == 0) ? kRowBytes + 16 : kRowBytes + 32; // odd multiple of 16 bytes
-    static constexpr int kLaneBytes = NB * kPitch;
-    static_assert((kPitch / 16) % 2 == 1, "row pitch must be an odd multiple of 16 bytes");
+    static constexpr int kRowBytes = S * 80;             // PCM bytes one lane produces per group
+    static constexpr int kTileBytes = 32 * kRowBytes;    // one warp's tile
+    static constexpr int kWarpBytes = NB * kTileBytes;
+    static constexpr int kInRing = 4;                    // 16-byte input vectors in flight per lane
+    static constexpr int kInWarpBytes = kInRing * 32 * 16; // slot-major: slot s of lane l at s*512 + l*16
+    static_assert(S % 2 == 1, "S must be odd (bank-conflict-free staging)");
+    static_assert(kTileBytes % 128 == 0, "TMA tiles must be 128-byte aligned");
 };
 
 __device__ __forceinline__ void bulk_store_s2g(void *gptr, uint32_t saddr, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(saddr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, uint32_t saddr, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+                 "r"(c1), "r"(saddr)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -367,6 +389,22 @@ __device__ __forceinline__ void bulk_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t saddr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -375,85 +413,161 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 template <int S, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
-                     const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
+                     const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
+                     const __grid_constant__ CUtensorMap out_map, int use_map)
 {
     using Cfg = StereoCfg<S, NB>;
+    constexpr uint32_t kFull = 0xffffffffu;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
     fill_lut(smem);
+    const uint32_t lane = threadIdx.x & 31;
     const uint64_t fi = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
-    if (fi >= n_frames) return;
-    const FrameRec rec = recs[fi];
-    const uint64_t ob = out_base[rec.stream];
-    const uint32_t nsamp = rec.nsamp;
-    if (nsamp == 0 || ob == ~0ull) return;
+
+    // ---- per-lane frame setup (lanes without work keep nslices == 0 and only take part in the warp-level steps)
+    uint32_t nsamp = 0;
+    uint64_t out_byte = 0; // byte offset of this frame's PCM inside the output arena
+    FrameRec rec;
+    rec.in_off = 0;
+    if (fi < n_frames) {
+        rec = recs[fi];
+        const uint64_t ob = out_base[rec.stream];
+        if (ob != ~0ull) {
+            nsamp = rec.nsamp;
+            out_byte = (ob + rec.out_rel) * 2;
+        }
+    }
+    const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
+    const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
+    if (nsl_max == 0) return;
+    const uint32_t nsamp_min = __reduce_min_sync(kFull, nsamp);
+    // regular warp: lane l's frame sits exactly l rows of 20480 bytes below lane 0's
+    const uint64_t out0 = __shfl_sync(kFull, out_byte, 0);
+    const bool regular = use_map && __all_sync(kFull, nsamp != 0 && out_byte == out0 + (uint64_t)lane * kOutRowBytes);
+    int map_c1 = (int)(out0 / kOutRowBytes);                 // tensor-map row of lane 0's frame start
+    int map_c0 = (int)((out0 % kOutRowBytes) / 4);           // 32-bit word inside that row
 
     const uint8_t *fp = arena + rec.in_off;
     Chain a, b;
-    load_lms(a, fp + 8);
-    load_lms(b, fp + 24);
     const uint8_t *sp = fp + 40;                                    // first slice word (8-byte aligned)
     const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 8);
     const uint4 *vp = reinterpret_cast<const uint4 *>(sp - skew);    // 16-byte aligned superset
-    const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
-    const uint32_t nvec = (skew + nslices * 16 + 15) / 16;          // vectors that hold any byte of this frame's slices
-    uint8_t *op = reinterpret_cast<uint8_t *>(out + ob + rec.out_rel);
-    const uint32_t lane_row = smem_u32(smem) + (threadIdx.x & 31) * 8;
-    const uint32_t stage = smem_u32(smem + kLutBytes) + threadIdx.x * Cfg::kLaneBytes;
+    const uint32_t nvec = nslices ? (skew + nslices * 16 + 15) / 16 : 0; // vectors holding any byte of this frame's slices
+    // input ring: vector j of this lane lives in slot j % 4; cp.async keeps three vectors in flight
+    const uint32_t in_ring = smem_u32(smem + kLutBytes) + (THREADS / 32) * Cfg::kWarpBytes +
+                             (threadIdx.x >> 5) * Cfg::kInWarpBytes + lane * 16;
+    auto fetch = [&](uint32_t j) {
+        if (j < nvec) cp_async16(in_ring + (j & 3) * 512, vp + j);
+        cp_async_commit();
+    };
+    fetch(0);
+    fetch(1);
+    fetch(2);
+    if (nslices) {
+        load_lms(a, fp + 8);
+        load_lms(b, fp + 24);
+    } else {
+        a = Chain{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
+        b = a;
+    }
+    uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
+    const uint32_t lane_row = smem_u32(smem) + lane * 8;
+    const uint32_t warp_tiles = smem_u32(smem + kLutBytes) + (threadIdx.x >> 5) * Cfg::kWarpBytes;
 
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    uint4 v0 = __ldg(vp);                       // vector holding the first half of the current slice pair
-    uint4 v1 = 1 < nvec ? __ldg(vp + 1) : zero; // the one after it
-    uint4 v2 = 2 < nvec ? __ldg(vp + 2) : zero; // prefetched
-    uint32_t ring = 0;                           // row of the ring being filled
-    uint32_t in_row = 0;                         // slices already staged in it
-    uint32_t first = 0;                          // per-channel sample index of the row's first sample
+    uint32_t ring = 0;   // tile of the ring being filled
+    uint32_t in_row = 0; // slices already staged in it
+    uint32_t first = 0;  // per-channel sample index of the tile's first sample
 
 #pragma unroll 1
-    for (uint32_t k = 0; k < nslices; ++k) {
-        uint32_t a_hi, a_lo, b_hi, b_lo;
-        if (skew) {
-            a_hi = v0.z; a_lo = v0.w; b_hi = v1.x; b_lo = v1.y;
-        } else {
-            a_hi = v0.x; a_lo = v0.y; b_hi = v0.z; b_lo = v0.w;
+    for (uint32_t k = 0; k < nsl_max; ++k) {
+        const uint32_t tile = warp_tiles + ring * Cfg::kTileBytes;
+        const uint32_t row = tile + lane * Cfg::kRowBytes;
+        if (in_row == 0) { // the copies that last read this tile have drained it
+            bulk_wait_read<NB - 1>();
+            __syncwarp();
         }
-        v0 = v1;
-        v1 = v2;
-        v2 = k + 3 < nvec ? __ldg(vp + k + 3) : zero;
-        const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
-        const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
-        const uint32_t row_a = lane_row + (wa.x >> 28) * 2048; // sf = top nibble (:303)
-        const uint32_t row_b = lane_row + (wb.x >> 28) * 2048;
-        const uint32_t row = stage + ring * Cfg::kPitch;
-        if (in_row == 0) bulk_wait_read<NB - 1>(); // the bulk copy that last read this row has drained it
-        uint32_t o[20];
-        PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-        const uint32_t dst_s = row + in_row * 80;
+        fetch(k + 3);
+        cp_async_wait<2>(); // vectors k and k + 1 have landed (only k + 2 and k + 3 may still be in flight)
+        if (k < nslices) {
+            // slice k = bytes [skew + 16k, skew + 16k + 16) of the vector stream: no alignment selects needed
+            const uint2 ra = lds64(in_ring + (k & 3) * 512 + skew);
+            const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
+            const uint32_t a_hi = ra.x, a_lo = ra.y, b_hi = rb.x, b_lo = rb.y;
+            const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
+            const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 2048; // sf = top nibble (:303)
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 2048;
+            uint32_t o[20];
+            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+            const uint32_t dst_s = row + in_row * 80;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
         ++in_row;
-        if (in_row == S || k + 1 == nslices) {
-            // hand the row to the TMA engine.  Samples past nsamp (partial last slice, :320-325) are not emitted.
-            const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * 4;
-            const uint32_t bulk = bytes & ~15u;
-            uint8_t *dst = op + (uint64_t)first * 4;
-            fence_async_smem();
-            if (bulk) bulk_store_s2g(dst, row, bulk);
-            bulk_commit();
-            if (bytes != bulk) { // 1..3 trailing (L, R) words of a frame whose sample count is not a multiple of 4
-                for (uint32_t t = bulk; t < bytes; t += 4) {
+        if (in_row == S || k + 1 == nsl_max) {
+            fence_async_smem(); // staging stores -> visible to the async proxy
+            __syncwarp();
+            const bool whole = regular && in_row == S && first + S * kSliceLen <= nsamp_min &&
+                               map_c0 + S * kSliceLen <= (int)(kOutRowBytes / 4);
+            if (whole) { // every lane staged S full slices: one tensor store for the warp
+                if (lane == 0) tensor_store_2d(&out_map, tile, map_c0, map_c1);
+            } else if (first < nsamp) {
+                // Samples past nsamp (partial last slice, :320-325) are not emitted.
+                const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * 4;
+                const uint32_t bulk = bytes & ~15u;
+                uint8_t *dst = op + (uint64_t)first * 4;
+                if (bulk) bulk_store_s2g(dst, row, bulk);
+                for (uint32_t t = bulk; t < bytes; t += 4) { // 1..3 trailing (L, R) words when nsamp % 4 != 0
                     uint32_t v;
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
                     *reinterpret_cast<uint32_t *>(dst + t) = v;
                 }
             }
+            bulk_commit();
             first += in_row * kSliceLen;
+            map_c0 += in_row * kSliceLen;
+            if (map_c0 >= (int)(kOutRowBytes / 4)) {
+                map_c0 -= (int)(kOutRowBytes / 4);
+                map_c1 += 1;
+            }
             in_row = 0;
             ring = (ring + 1 == NB) ? 0 : ring + 1;
         }
     }
-    bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read every row
+    bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read every tile
+}
+
+// Encodes the tensor map that views the output arena as rows of 20480 bytes (one full stereo frame) of 32-bit words;
+// box = box_words x 32 rows.  Returns false when the driver entry point is unavailable or the arena does not qualify
+// (the kernel then uses per-lane bulk copies only).
+static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked_up = false;
+    if (!looked_up) {
+        looked_up = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode || (reinterpret_cast<uintptr_t>(d_out) & 15) || out_bytes == 0) return false;
+    const uint64_t rows = (out_bytes + kOutRowBytes - 1) / kOutRowBytes;
+    if (rows > 0x7fffffffull) return false;
+    const cuuint64_t dims[2] = {kOutRowBytes / 4, rows};
+    const cuuint64_t strides[1] = {kOutRowBytes};
+    const cuuint32_t box[2] = {box_words, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
@@ -501,9 +615,10 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
 
 template <int S, int NB, int THREADS>
 static cudaError_t launch_stereo(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
-                                 const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s)
+                                 const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
 {
-    const size_t smem = kLutAlign + kLutBytes + (size_t)THREADS * StereoCfg<S, NB>::kLaneBytes;
+    const size_t smem = kLutAlign + kLutBytes +
+                        (size_t)(THREADS / 32) * (StereoCfg<S, NB>::kWarpBytes + StereoCfg<S, NB>::kInWarpBytes);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(decode_stereo_kernel<S, NB, THREADS>,
@@ -511,15 +626,19 @@ static cudaError_t launch_stereo(const uint8_t *d_arena, const FrameRec *d_recs,
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    const int use_map = make_out_map(&map, d_out, out_bytes, S * kSliceLen) ? 1 : 0;
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     decode_stereo_kernel<S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
-                                                                                 d_out);
+                                                                                 d_out, map, use_map);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
-                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s, int *n_launches)
+                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
+                          cudaStream_t s, int *n_launches)
 {
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
     cudaError_t e;
@@ -531,12 +650,12 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
             variant = v ? atoi(v) : 0;
         }
         switch (variant) {
-        case 1: e = launch_stereo<4, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
-        case 2: e = launch_stereo<4, 2, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
-        case 3: e = launch_stereo<3, 2, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
-        case 4: e = launch_stereo<2, 2, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
-        case 5: e = launch_stereo<8, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
-        default: e = launch_stereo<2, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, s); break;
+        case 1: e = launch_stereo<3, 2, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 2: e = launch_stereo<5, 1, 416>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 3: e = launch_stereo<3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 4: e = launch_stereo<1, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 5: e = launch_stereo<7, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        default: e = launch_stereo<3, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         }
     } else {
         const uint64_t n_units = n_frames * max_ch;

@@ -18,9 +18,11 @@ cudaError_t launch_index_count(const uint8_t *d_arena, const uint64_t *d_in_off,
 cudaError_t launch_index_fill(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
                               int mode, const uint64_t *d_frame_base, FrameRec *d_recs, cudaStream_t s);
 // Frame-parallel decode.  max_ch = largest channel count of any frame in the table; d_out_base[stream] = i16 element
-// offset of the stream's output in d_out (UINT64_MAX = do not write this stream).
+// offset of the stream's output in d_out (UINT64_MAX = do not write this stream); out_bytes = extent of the output arena
+// that the batch may touch (upper bound of any written byte offset).
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
-                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, cudaStream_t s, int *n_launches);
+                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
+                          cudaStream_t s, int *n_launches);
 
 // ---- encode --------------------------------------------------------------------------------------------------
 // Per-stream encode job (device table).
