@@ -307,15 +307,43 @@ __device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, 
     return r;
 }
 
+// Both channels of one sample.  The two reconstructed values are clamped to i16 AND packed into the (L, R) output
+// word by one I2IP (cvt.pack.sat.s16.s32); the clamped values are then read back out of the packed word for the LMS
+// history.  Same arithmetic as decode_step, two instructions fewer per sample pair.
+template <int I>
+__device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb)
+{
+    const int2 ta = lds_v2(row_a | code_off<I>(wa.x, wa.y)); // {dequantized, delta}
+    const int2 tb = lds_v2(row_b | code_off<I>(wb.x, wb.y));
+    const int xa = ((a.w0 * a.h0 + a.w1 * a.h1 + a.w2 * a.h2 + a.w3 * a.h3) >> 13) + ta.x; // predict :799-805, :310
+    const int xb = ((b.w0 * b.h0 + b.w1 * b.h1 + b.w2 * b.h2 + b.w3 * b.h3) >> 13) + tb.x;
+    uint32_t packed; // (clamp_i16(xb) << 16) | (clamp_i16(xa) & 0xffff)
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(xb), "r"(xa));
+    int ra; // sign-extend the low half: selector nibble 9 = replicate the sign of byte 1
+    asm("prmt.b32 %0, %1, %1, 0x9910;" : "=r"(ra) : "r"(packed));
+    const int rb = (int)packed >> 16;
+    a.w0 += a.s0 * ta.y; // update :821-828
+    a.w1 += a.s1 * ta.y;
+    a.w2 += a.s2 * ta.y;
+    a.w3 += a.s3 * ta.y;
+    b.w0 += b.s0 * tb.y;
+    b.w1 += b.s1 * tb.y;
+    b.w2 += b.s2 * tb.y;
+    b.w3 += b.s3 * tb.y;
+    a.h0 = a.h1; a.h1 = a.h2; a.h2 = a.h3; a.h3 = ra;
+    b.h0 = b.h1; b.h1 = b.h2; b.h2 = b.h3; b.h3 = rb;
+    a.s0 = a.s1; a.s1 = a.s2; a.s2 = a.s3; a.s3 = sign_pm1(ra);
+    b.s0 = b.s1; b.s1 = b.s2; b.s2 = b.s3; b.s3 = sign_pm1(rb);
+    return packed;
+}
+
 template <int I>
 struct PairLoop {
     // Decodes samples I..19 of a slice for two channels; o[i] = (r_b << 16) | (r_a & 0xffff).
     static __device__ __forceinline__ void run(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb,
                                                uint32_t *o)
     {
-        const int ra = decode_step<I>(a, row_a, wa.x, wa.y);
-        const int rb = decode_step<I>(b, row_b, wb.x, wb.y);
-        o[I] = __byte_perm((uint32_t)ra, (uint32_t)rb, 0x5410);
+        o[I] = decode_pair_step<I>(a, b, row_a, row_b, wa, wb);
         PairLoop<I + 1>::run(a, b, row_a, row_b, wa, wb, o);
     }
 };
@@ -650,11 +678,15 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
             variant = v ? atoi(v) : 0;
         }
         switch (variant) {
-        case 1: e = launch_stereo<3, 2, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 2: e = launch_stereo<5, 1, 416>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 3: e = launch_stereo<3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 4: e = launch_stereo<1, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 5: e = launch_stereo<7, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 1: e = launch_stereo<3, 1, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 2: e = launch_stereo<3, 1, 448>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 3: e = launch_stereo<3, 1, 480>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 4: e = launch_stereo<3, 1, 544>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 5: e = launch_stereo<3, 1, 576>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 6: e = launch_stereo<5, 1, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 7: e = launch_stereo<5, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 8: e = launch_stereo<1, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 9: e = launch_stereo<1, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         default: e = launch_stereo<3, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         }
     } else {

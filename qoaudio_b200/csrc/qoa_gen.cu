@@ -94,6 +94,15 @@ cudaError_t launch_gen_qoa(uint8_t *d_qoa, uint64_t stride, uint64_t n_streams, 
 
 // ---- integer issue-rate microbenchmark -----------------------------------------------------------------------
 // 8 independent dependency chains per thread, 16 warps per SM x 4 CTAs: enough to saturate every scheduler.
+// kind 0 = IMAD, 1 = LOP3, 2 = IMAD + LOP3 1:1 (the two-pipe issue peak).  Kinds >= 3 time single SASS opcodes the
+// kernels lean on (development aid): 3 I2IP.SAT, 4 VIMNMX, 5 SHF, 6 PRMT, 7 LEA.HI, 8 IMAD.HI, 9 IADD3, 10 SEL-free
+// ISETP+SEL pair, 11 IMAD.WIDE.
+#define QOA_OP8(STMT)                                                                                              \
+    do {                                                                                                           \
+        { int &x = x0; STMT; } { int &x = x1; STMT; } { int &x = x2; STMT; } { int &x = x3; STMT; }                \
+        { int &x = x4; STMT; } { int &x = x5; STMT; } { int &x = x6; STMT; } { int &x = x7; STMT; }                \
+    } while (0);
+
 template <int KIND>
 __global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int a, int b)
 {
@@ -101,34 +110,48 @@ __global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (KIND == 0 || KIND == 2) { // IMAD
+            if (KIND == 0) QOA_OP8(asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 1) QOA_OP8(asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 2) {
                 asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
-            }
-            if (KIND == 0) {
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
-                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
-            }
-            if (KIND == 1) { // LOP3
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(a), "r"(b));
-            }
-            if (KIND == 1 || KIND == 2) {
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+            if (KIND == 3) QOA_OP8(asm volatile("cvt.pack.sat.s16.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 4) QOA_OP8(asm volatile("min.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 5) QOA_OP8(asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 6) QOA_OP8(asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 7) QOA_OP8(asm volatile("{ .reg .s32 t; shr.s32 t, %0, 13; add.s32 %0, t, %1; }" : "+r"(x) : "r"(a)))
+            if (KIND == 8) QOA_OP8(asm volatile("mad.hi.s32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 9) QOA_OP8(asm volatile("add.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 10) QOA_OP8(asm volatile("{ .reg .pred p; setp.lt.s32 p, %0, %1; selp.s32 %0, %2, %0, p; }" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 11) {
+                long long y = x0;
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x1), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x2), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x3), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x4), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x5), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x6), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x7), "r"(a));
+                asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x1), "r"(b));
+                x0 = (int)y ^ (int)(y >> 32);
             }
         }
     }
     const int r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
     if (r == 0x7fffffff) out[0] = r; // practically never; keeps the chains alive
+}
+
+template <int KIND>
+static void launch_issue(int grid, int block, int *d_out, int iters)
+{
+    int_issue_kernel<KIND><<<grid, block>>>(d_out, iters, 3, 7);
 }
 
 cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
@@ -143,9 +166,20 @@ cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
     float best_ms = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(t0);
-        if (kind == 0) int_issue_kernel<0><<<grid, block>>>(d_out, iters, 3, 7);
-        else if (kind == 1) int_issue_kernel<1><<<grid, block>>>(d_out, iters, 3, 7);
-        else int_issue_kernel<2><<<grid, block>>>(d_out, iters, 3, 7);
+        switch (kind) {
+        case 0: launch_issue<0>(grid, block, d_out, iters); break;
+        case 1: launch_issue<1>(grid, block, d_out, iters); break;
+        case 2: launch_issue<2>(grid, block, d_out, iters); break;
+        case 3: launch_issue<3>(grid, block, d_out, iters); break;
+        case 4: launch_issue<4>(grid, block, d_out, iters); break;
+        case 5: launch_issue<5>(grid, block, d_out, iters); break;
+        case 6: launch_issue<6>(grid, block, d_out, iters); break;
+        case 7: launch_issue<7>(grid, block, d_out, iters); break;
+        case 8: launch_issue<8>(grid, block, d_out, iters); break;
+        case 9: launch_issue<9>(grid, block, d_out, iters); break;
+        case 10: launch_issue<10>(grid, block, d_out, iters); break;
+        default: launch_issue<11>(grid, block, d_out, iters); break;
+        }
         cudaEventRecord(t1);
         e = cudaEventSynchronize(t1);
         if (e != cudaSuccess) break;
@@ -157,7 +191,7 @@ cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
     cudaEventDestroy(t1);
     cudaFree(d_out);
     if (e != cudaSuccess) return e;
-    const double ops = (double)grid * block * (double)iters * 64.0;
+    const double ops = (double)grid * block * (double)iters * 64.0; // 8 unrolled x 8 chains per iteration
     *thread_ops_per_s = ops / (best_ms * 1e-3);
     return cudaGetLastError();
 }

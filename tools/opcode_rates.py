@@ -1,0 +1,9 @@
+"""Per-opcode integer throughput on the current GPU (development aid for the kernel instruction diet)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qoaudio_b200 as q
+eng = q.Engine(0)
+names = ["IMAD", "LOP3", "IMAD+LOP3 1:1", "I2IP.SAT", "VIMNMX", "SHF", "PRMT", "LEA.HI.SX32", "IMAD.HI", "IADD3/IMAD.IADD",
+         "ISETP+SEL", "IMAD.WIDE"]
+for k, n in enumerate(names):
+    print(f"{k:2d} {n:18s} {eng.int_issue_peak(k) / 1e12:7.2f} T thread-ops/s")
