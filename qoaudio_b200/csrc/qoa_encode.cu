@@ -12,94 +12,124 @@
 // (the reference's pruning never changes the winner: ranks are monotone).  The winner is the lexicographic minimum of
 // (total rank, first-sample rank, scalefactor) — exactly what the reference's stable insertion sort by first-sample
 // rank (:535-541) followed by strict `<` replacement (:587) selects.
+//
+// Instruction diet (B200 issues IMAD on the FMA pipe and everything else on the ALU pipe, each at half rate, so the
+// step is balanced between the two): the +/-1 sign of every history tap is kept in a register so the weight update is
+// four IMADs; the LUT returns {dequantized, quantized, delta} in one 128-bit shared load; clamp/add pairs use the
+// fused VIADDMNMX; the squared error accumulates through one IMAD.WIDE; the 3-bit codes accumulate in two 30-bit
+// halves; PCM samples are staged de-interleaved in shared memory 16 slices at a time so the per-step fetch is one
+// broadcast LDS with an immediate offset.
 #include "qoa_kernels.h"
 
 namespace qoa {
 
-constexpr int kEncThreads = 128; // 4 warps = 8 chains per CTA
+constexpr int kEncThreads = 128;                         // 4 warps = 8 chains per CTA
+constexpr int kEncWarps = kEncThreads / 32;
+constexpr int kChunkSlices = 16;                         // slices staged per refill
+constexpr int kChunkSamples = kChunkSlices * kSliceLen;  // 320 samples per chain
+constexpr uint32_t kFull = 0xffffffffu;
 
-// Candidate LUT in shared memory: entry idx = clamp(scaled, -8, 8) + 8 of scalefactor sf at byte (idx * 16 + sf) * 8,
-// holding {dequantized, quantized}.  A half-warp (16 scalefactors) reads 16 consecutive 8-byte words: conflict-free.
-struct __align__(16) EncLut {
-    int2 v[17 * 16];
+// Candidate LUT: entry (idx, sf), idx = clamp(scaled, -8, 8) + 8, at byte (idx * 16 + sf) * 16 holding
+// {dequantized, quantized, dequantized >> 4, 0}.  A quarter-warp (8 scalefactors) reads 8 distinct 16-byte bank groups
+// whatever the indices are: conflict-free.
+struct __align__(16) EncSmem {
+    int4 lut[17 * 16];
+    int16_t stage[kEncWarps][2][kChunkSamples];
 };
 
-struct Lms {
+struct Cand {
     int h0, h1, h2, h3;
     int w0, w1, w2, w3;
+    int s0, s1, s2, s3; // +1 / -1: the sign update() derives from history (:823-826; zero counts as positive)
 };
 
-// qoa_div :613-617 — wrapping multiply, round half up, then push away from zero.
-__device__ __forceinline__ int qoa_div(int v, int recip)
-{
-    const int n = (int)((uint32_t)v * (uint32_t)recip + 32768u) >> 16;
-    const int sv = max(-1, min(1, v)); // (v > 0) - (v < 0)
-    const int sn = max(-1, min(1, n));
-    return n + sv - sn;
-}
+__device__ __forceinline__ int sign_pm1(int v) { return (v >> 31) | 1; }
 
-// One (candidate, sample) step :564-585.  Returns the rank contribution err^2 + penalty^2 (< 2^33).
-__device__ __forceinline__ uint64_t candidate_step(Lms &l, int s, int recip, uint32_t lut_lane, uint32_t &codes)
+// One (candidate, sample) step :564-585.  err accumulates error^2 (64-bit), pen accumulates penalty^2 (fits 32 bits:
+// penalty < 2^13, 20 terms), codes accumulates the 3-bit quantized values.
+__device__ __forceinline__ void candidate_step(Cand &l, int s, int recip, uint32_t lut_lane, long long &err, uint32_t &pen,
+                                               uint32_t &codes)
 {
     // predict_and_penalty_sq :808-818 (all sums wrap in i32)
     const int p = (l.w0 * l.h0 + l.w1 * l.h1 + l.w2 * l.h2 + l.w3 * l.h3) >> 13;
     const int ws = (l.w0 * l.w0 + l.w1 * l.w1 + l.w2 * l.w2 + l.w3 * l.w3) >> 18;
-    const int pen = max(ws - 0x8ff, 0);
-    const int v = s - p;                                 // :567
-    const int c = max(-8, min(8, qoa_div(v, recip)));    // :568-569
-    int dq, q;
-    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(dq), "=r"(q) : "r"(lut_lane + (uint32_t)(c + 8) * 128u)); // :570-572
-    const int r = clamp_i16(p + dq);                     // :573
-    const int e = s - r;                                 // :575
-    const uint64_t rank = (uint64_t)((int64_t)e * (int64_t)e) + (uint64_t)((uint32_t)pen * (uint32_t)pen); // :576
-    const int d = dq >> 4;                               // update :821-828
-    l.w0 += l.h0 < 0 ? -d : d;
-    l.w1 += l.h1 < 0 ? -d : d;
-    l.w2 += l.h2 < 0 ? -d : d;
-    l.w3 += l.h3 < 0 ? -d : d;
-    l.h0 = l.h1;
-    l.h1 = l.h2;
-    l.h2 = l.h3;
-    l.h3 = r;
-    codes = (codes << 3) | (uint32_t)q;                  // :584
-    return rank;
+    const int penalty = __viaddmax_s32(ws, -0x8ff, 0);
+    const int v = s - p; // :567
+    // qoa_div :613-617 — wrapping multiply, round half up, then push away from zero
+    const int n = (int)((uint32_t)v * (uint32_t)recip + 32768u) >> 16;
+    const int t = n + max(-1, min(1, v)) - max(-1, min(1, n));
+    const int c = max(-8, min(8, t)); // :568-569
+    int dq, q, d, unused;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(dq), "=r"(q), "=r"(d), "=r"(unused)
+                 : "r"(lut_lane + (uint32_t)(c * 256))); // :570-572 (lut_lane is pre-biased by +8 entries)
+    const int r = max(__viaddmin_s32(p, dq, 32767), -32768); // :573
+    const int e = s - r;                                     // :575
+    err += (long long)e * (long long)e;                      // :576
+    pen += (uint32_t)penalty * (uint32_t)penalty;
+    l.w0 += l.s0 * d; // update :821-828 (d = dequantized >> 4)
+    l.w1 += l.s1 * d;
+    l.w2 += l.s2 * d;
+    l.w3 += l.s3 * d;
+    l.h0 = l.h1; l.h1 = l.h2; l.h2 = l.h3; l.h3 = r;
+    l.s0 = l.s1; l.s1 = l.s2; l.s2 = l.s3; l.s3 = sign_pm1(r);
+    codes = codes * 8u + (uint32_t)q; // :584
 }
 
-struct Key {
-    uint64_t total, first;
-    uint32_t sf;
-};
-__device__ __forceinline__ bool key_less(const Key &a, const Key &b)
+__device__ __forceinline__ int lds_s16(uint32_t addr)
 {
-    if (a.total != b.total) return a.total < b.total;
-    if (a.first != b.first) return a.first < b.first;
-    return a.sf < b.sf;
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Lexicographic (total, first, sf) arg-min over a half-warp; only used when two candidates tie on the total rank.
+__device__ __noinline__ uint32_t winner_slow(uint64_t total, uint64_t first, uint32_t sf)
+{
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) {
+        const uint64_t ot = __shfl_xor_sync(kFull, total, m);
+        const uint64_t of = __shfl_xor_sync(kFull, first, m);
+        const uint32_t os = __shfl_xor_sync(kFull, sf, m);
+        const bool less = ot != total ? ot < total : (of != first ? of < first : os < sf);
+        if (less) {
+            total = ot;
+            first = of;
+            sf = os;
+        }
+    }
+    return sf;
 }
 
 // One warp = two chains (half-warps).  Both halves run the same number of iterations (the longer chain's slice count);
-// a half whose chain is exhausted computes on zeros and stores nothing, so every shuffle is warp-converged.
-__global__ void __launch_bounds__(kEncThreads)
+// a half whose chain is exhausted computes on zeros and commits nothing, so every shuffle is warp-converged.
+__global__ void __launch_bounds__(kEncThreads, 7)
 encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncJob *__restrict__ jobs,
               const EncChain *__restrict__ chains, uint32_t n_chains, int32_t *__restrict__ lms_state)
 {
-    __shared__ EncLut lut;
+    __shared__ EncSmem sm;
     for (int i = threadIdx.x; i < 17 * 16; i += kEncThreads) {
         const int idx = i >> 4, sf = i & 15;
         const int q = c_quant[idx];
-        lut.v[i] = make_int2(c_dequant[sf * 8 + q], q);
+        const int dq = c_dequant[sf * 8 + q];
+        sm.lut[i] = make_int4(dq, q, dq >> 4, 0);
     }
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sf = lane & 15;
+    const uint32_t half = lane >> 4;
+    const uint32_t warp_in_cta = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * kEncThreads + threadIdx.x) >> 5;
-    const uint32_t chain = warp * 2 + (lane >> 4);
+    const uint32_t chain = warp * 2 + half;
     const bool have_chain = chain < n_chains;
-    const uint32_t lut_lane = smem_u32(&lut.v[0]) + sf * 8;
+    const uint32_t lut_lane = smem_u32(&sm.lut[0]) + sf * 16 + 8 * 256;
+    const uint32_t stage = smem_u32(&sm.stage[warp_in_cta][half][0]);
     const int recip = c_recip[sf];
 
     EncJob job;
-    job.pcm_off = 0; job.out_off = 0; job.channels = 1; job.rate = 0; job.nsamples = 0; job.lms_base = 0; job.file_samples = 0; job.flags = 0;
+    job.pcm_off = 0; job.out_off = 0; job.channels = 1; job.rate = 0; job.nsamples = 0; job.lms_base = 0;
+    job.file_samples = 0; job.flags = 0;
     uint32_t c = 0;
     if (have_chain) {
         const EncChain ec = chains[chain];
@@ -109,12 +139,11 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
     const uint32_t ch = job.channels;
     const uint32_t n = job.nsamples;
     const uint32_t my_slices = (n + kSliceLen - 1) / kSliceLen;
-    const uint32_t other_slices = __shfl_xor_sync(0xffffffffu, my_slices, 16);
-    const uint32_t total_slices = max(my_slices, other_slices);
+    const uint32_t total_slices = max(my_slices, __shfl_xor_sync(kFull, my_slices, 16));
     if (total_slices == 0) return; // both chains of this warp idle
 
     int32_t *st = lms_state + (size_t)(job.lms_base + c) * 8;
-    Lms cur;
+    Cand cur;
     if (my_slices) {
         cur.h0 = st[0]; cur.h1 = st[1]; cur.h2 = st[2]; cur.h3 = st[3];
         cur.w0 = st[4]; cur.w1 = st[5]; cur.w2 = st[6]; cur.w3 = st[7];
@@ -122,6 +151,7 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
         cur.h0 = cur.h1 = cur.h2 = cur.h3 = 0;
         cur.w0 = cur.w1 = cur.w2 = cur.w3 = 0;
     }
+    cur.s0 = sign_pm1(cur.h0); cur.s1 = sign_pm1(cur.h1); cur.s2 = sign_pm1(cur.h2); cur.s3 = sign_pm1(cur.h3);
 
     const int16_t *src = pcm + job.pcm_off + c;
     uint8_t *frames_out = out + job.out_off;
@@ -131,10 +161,26 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
     }
     const size_t full_frame_bytes = 8 + 16 * (size_t)ch + 8 * (size_t)kSlicesPerFrame * ch; // qoa_frame_size :602-604
 
+#pragma unroll 1
     for (uint32_t j = 0; j < total_slices; ++j) {
+        // ---- stage the next 16 slices of this chain, de-interleaved (:502-508), zero-filled past the end
+        if ((j & (kChunkSlices - 1)) == 0) {
+            __syncwarp();
+            const uint32_t base = j * kSliceLen + sf;
+            int v[kChunkSamples / 16];
+#pragma unroll
+            for (int m = 0; m < kChunkSamples / 16; ++m) {
+                const uint32_t s = base + 16 * m;
+                v[m] = s < n ? (int)__ldg(src + (size_t)s * ch) : 0;
+            }
+#pragma unroll
+            for (int m = 0; m < kChunkSamples / 16; ++m)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(stage + (sf + 16 * m) * 2), "h"((short)v[m]) : "memory");
+            __syncwarp();
+        }
         const bool active = j < my_slices;
         const uint32_t f = j >> 8, k = j & 255;
-        const uint32_t s0 = j * kSliceLen;                       // first sample (per channel) of this slice
+        const uint32_t s0 = j * kSliceLen; // first sample (per channel) of this slice
         const uint32_t len = active ? min((uint32_t)kSliceLen, n - s0) : 0u;
         uint8_t *frame = frames_out + (size_t)f * full_frame_bytes;
 
@@ -142,66 +188,77 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
             const uint32_t frame_len = min((uint32_t)kFrameLen, n - f * kFrameLen);
             const uint32_t slices = (frame_len + kSliceLen - 1) / kSliceLen;
             const uint32_t frame_size = (8 + 16 * ch + 8 * slices * ch) & 0xffffu; // `as u16`
-            if (c == 0) st_be64(frame, (ch << 24) | job.rate, (frame_len << 16) | frame_size); // rate is OR-ed unmasked like :449
+            if (c == 0) st_be64(frame, (ch << 24) | job.rate, (frame_len << 16) | frame_size); // rate OR-ed unmasked (:449)
             uint8_t *lp = frame + 8 + 16 * c; // truncating `as u16` dump of the carried i32 state :459-460
             st_be64(lp, ((uint32_t)cur.h0 << 16) | ((uint32_t)cur.h1 & 0xffffu), ((uint32_t)cur.h2 << 16) | ((uint32_t)cur.h3 & 0xffffu));
             st_be64(lp + 8, ((uint32_t)cur.w0 << 16) | ((uint32_t)cur.w1 & 0xffffu), ((uint32_t)cur.w2 << 16) | ((uint32_t)cur.w3 & 0xffffu));
         }
 
-        // the candidate: every lane runs all `len` samples with its own scalefactor
-        Lms l = cur;
-        uint64_t total = 0, first = 0;
+        // ---- the candidates: every lane runs the slice with its own scalefactor
+        Cand l = cur;
+        long long err = 0;
+        uint32_t pen = 0, first_err = 0, first_pen = 0;
         uint32_t codes_a = 0, codes_b = 0; // samples 0..9 and 10..19, 3 bits each
-        if (len == kSliceLen) {
-            const int16_t *sp = src + (size_t)s0 * ch;
+        const uint32_t sp = stage + (j & (kChunkSlices - 1)) * (kSliceLen * 2);
+        if (__all_sync(kFull, len == kSliceLen || !active)) { // steady state (an idle half computes on zeros)
+            candidate_step(l, lds_s16(sp), recip, lut_lane, err, pen, codes_a);
+            first_err = (uint32_t)err; // error^2 of one sample fits 32 bits
+            first_pen = pen;
 #pragma unroll
-            for (int i = 0; i < 10; ++i) {
-                const uint64_t r = candidate_step(l, (int)__ldg(sp + (size_t)i * ch), recip, lut_lane, codes_a);
-                if (i == 0) first = r;
-                total += r;
-            }
+            for (int i = 1; i < 10; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_a);
 #pragma unroll
-            for (int i = 10; i < 20; ++i) total += candidate_step(l, (int)__ldg(sp + (size_t)i * ch), recip, lut_lane, codes_b);
-        } else {
-            const int16_t *sp = src + (size_t)s0 * ch;
-            for (uint32_t i = 0; i < len; ++i) {
-                const uint64_t r = candidate_step(l, (int)__ldg(sp + (size_t)i * ch), recip, lut_lane, i < 10 ? codes_a : codes_b);
-                if (i == 0) first = r;
-                total += r;
+            for (int i = 10; i < 20; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_b);
+        } else { // a partial last slice somewhere in the warp
+#pragma unroll 1
+            for (uint32_t i = 0; i < kSliceLen; ++i) {
+                if (i < len) {
+                    candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, i < 10 ? codes_a : codes_b);
+                    if (i == 0) {
+                        first_err = (uint32_t)err;
+                        first_pen = pen;
+                    }
+                }
             }
             // left-justify: the reference shifts the whole word by (20 - len) * 3 (:485-487)
-            if (len <= 10) {
+            if (len <= 10)
                 codes_a <<= (10 - len) * 3;
-            } else {
+            else
                 codes_b <<= (20 - len) * 3;
-            }
         }
 
-        // winner within the half-warp: lexicographic min of (total, first, sf)
-        Key best{total, first, sf};
+        // ---- winner within the half-warp: min total rank; ties (rare) resolved by (first-sample rank, sf)
+        const uint64_t total = (uint64_t)err + pen;
+        uint32_t hi = (uint32_t)(total >> 32), lo = (uint32_t)total;
+        uint32_t mh = hi;
+        if (__any_sync(kFull, hi != 0)) {
 #pragma unroll
-        for (int m = 8; m >= 1; m >>= 1) {
-            Key o;
-            o.total = __shfl_xor_sync(0xffffffffu, best.total, m);
-            o.first = __shfl_xor_sync(0xffffffffu, best.first, m);
-            o.sf = __shfl_xor_sync(0xffffffffu, best.sf, m);
-            if (key_less(o, best)) best = o;
+            for (int m = 8; m >= 1; m >>= 1) mh = min(mh, __shfl_xor_sync(kFull, mh, m));
+            if (hi != mh) lo = 0xffffffffu; // out of the race (a true 0xffffffff with hi == mh still ties correctly below)
         }
-        const int src_lane = (int)((lane & 16) | best.sf);
-        cur.h0 = __shfl_sync(0xffffffffu, l.h0, src_lane);
-        cur.h1 = __shfl_sync(0xffffffffu, l.h1, src_lane);
-        cur.h2 = __shfl_sync(0xffffffffu, l.h2, src_lane);
-        cur.h3 = __shfl_sync(0xffffffffu, l.h3, src_lane);
-        cur.w0 = __shfl_sync(0xffffffffu, l.w0, src_lane);
-        cur.w1 = __shfl_sync(0xffffffffu, l.w1, src_lane);
-        cur.w2 = __shfl_sync(0xffffffffu, l.w2, src_lane);
-        cur.w3 = __shfl_sync(0xffffffffu, l.w3, src_lane);
-
-        if (active && sf == best.sf) { // the winning lane packs and stores its slice :488-489
-            // word = sf:4 | codes_a:30 | codes_b:30
-            const uint64_t word = ((uint64_t)sf << 60) | ((uint64_t)codes_a << 30) | (uint64_t)codes_b;
-            uint8_t *dst = frame + 8 + 16 * (size_t)ch + ((size_t)k * ch + c) * 8;
-            st_be64(dst, (uint32_t)(word >> 32), (uint32_t)word);
+        uint32_t ml = lo;
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1) ml = min(ml, __shfl_xor_sync(kFull, ml, m));
+        const bool is_min = hi == mh && (uint32_t)total == ml;
+        const uint32_t votes = (__ballot_sync(kFull, is_min) >> (half * 16)) & 0xffffu;
+        uint32_t win = __ffs(votes) - 1;
+        if (__any_sync(kFull, (votes & (votes - 1)) != 0)) // some half has a tie on the total rank
+            win = winner_slow(total, (uint64_t)first_err + first_pen, sf);
+        const int src_lane = (int)((lane & 16) | win);
+        const int nh0 = __shfl_sync(kFull, l.h0, src_lane), nh1 = __shfl_sync(kFull, l.h1, src_lane);
+        const int nh2 = __shfl_sync(kFull, l.h2, src_lane), nh3 = __shfl_sync(kFull, l.h3, src_lane);
+        const int nw0 = __shfl_sync(kFull, l.w0, src_lane), nw1 = __shfl_sync(kFull, l.w1, src_lane);
+        const int nw2 = __shfl_sync(kFull, l.w2, src_lane), nw3 = __shfl_sync(kFull, l.w3, src_lane);
+        const int ns0 = __shfl_sync(kFull, l.s0, src_lane), ns1 = __shfl_sync(kFull, l.s1, src_lane);
+        const int ns2 = __shfl_sync(kFull, l.s2, src_lane), ns3 = __shfl_sync(kFull, l.s3, src_lane);
+        if (active) { // carry the winner's full i32 state (:481-482)
+            cur.h0 = nh0; cur.h1 = nh1; cur.h2 = nh2; cur.h3 = nh3;
+            cur.w0 = nw0; cur.w1 = nw1; cur.w2 = nw2; cur.w3 = nw3;
+            cur.s0 = ns0; cur.s1 = ns1; cur.s2 = ns2; cur.s3 = ns3;
+            if (sf == win) { // the winning lane packs and stores its slice :488-489: sf:4 | codes_a:30 | codes_b:30
+                const uint32_t word_hi = (sf << 28) | (codes_a >> 2);
+                const uint32_t word_lo = (codes_a << 30) | codes_b;
+                st_be64(frame + 8 + 16 * (size_t)ch + ((size_t)k * ch + c) * 8, word_hi, word_lo);
+            }
         }
     }
 
@@ -216,7 +273,7 @@ cudaError_t launch_encode(const int16_t *d_pcm, uint8_t *d_out, const EncJob *d_
 {
     if (n_chains == 0) return cudaSuccess;
     const uint32_t warps = (n_chains + 1) / 2;
-    const uint32_t blocks = (warps * 32 + kEncThreads - 1) / kEncThreads;
+    const uint32_t blocks = (warps + kEncWarps - 1) / kEncWarps;
     encode_kernel<<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
