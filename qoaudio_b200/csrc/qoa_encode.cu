@@ -47,14 +47,16 @@ __device__ __forceinline__ int sign_pm1(int v) { return (v >> 31) | 1; }
 
 // One (candidate, sample) step :564-585.  err accumulates error^2 (64-bit), pen accumulates penalty^2 (fits 32 bits:
 // penalty < 2^13, 20 terms), codes accumulates the 3-bit quantized values.
+// `zero` is an opaque 0 (a kernel argument): a three-input add can only issue as IADD3 on the ALU pipe, which keeps the
+// two subtractions off the FMA pipe (the busier one in this step: 14 IMADs + the wide multiply-add).
 __device__ __forceinline__ void candidate_step(Cand &l, int s, int recip, uint32_t lut_lane, long long &err, uint32_t &pen,
-                                               uint32_t &codes)
+                                               uint32_t &codes, int zero)
 {
     // predict_and_penalty_sq :808-818 (all sums wrap in i32)
     const int p = (l.w0 * l.h0 + l.w1 * l.h1 + l.w2 * l.h2 + l.w3 * l.h3) >> 13;
     const int ws = (l.w0 * l.w0 + l.w1 * l.w1 + l.w2 * l.w2 + l.w3 * l.w3) >> 18;
     const int penalty = __viaddmax_s32(ws, -0x8ff, 0);
-    const int v = s - p; // :567
+    const int v = s - p + zero; // :567
     // qoa_div :613-617 — wrapping multiply, round half up, then push away from zero
     const int n = (int)((uint32_t)v * (uint32_t)recip + 32768u) >> 16;
     const int t = n + max(-1, min(1, v)) - max(-1, min(1, n));
@@ -64,7 +66,7 @@ __device__ __forceinline__ void candidate_step(Cand &l, int s, int recip, uint32
                  : "=r"(dq), "=r"(q), "=r"(d), "=r"(unused)
                  : "r"(lut_lane + (uint32_t)(c * 256))); // :570-572 (lut_lane is pre-biased by +8 entries)
     const int r = max(__viaddmin_s32(p, dq, 32767), -32768); // :573
-    const int e = s - r;                                     // :575
+    const int e = s - r + zero;                              // :575
     err += (long long)e * (long long)e;                      // :576
     pen += (uint32_t)penalty * (uint32_t)penalty;
     l.w0 += l.s0 * d; // update :821-828 (d = dequantized >> 4)
@@ -105,7 +107,7 @@ __device__ __noinline__ uint32_t winner_slow(uint64_t total, uint64_t first, uin
 // a half whose chain is exhausted computes on zeros and commits nothing, so every shuffle is warp-converged.
 __global__ void __launch_bounds__(kEncThreads, 7)
 encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncJob *__restrict__ jobs,
-              const EncChain *__restrict__ chains, uint32_t n_chains, int32_t *__restrict__ lms_state)
+              const EncChain *__restrict__ chains, uint32_t n_chains, int32_t *__restrict__ lms_state, int zero)
 {
     __shared__ EncSmem sm;
     for (int i = threadIdx.x; i < 17 * 16; i += kEncThreads) {
@@ -201,18 +203,18 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
         uint32_t codes_a = 0, codes_b = 0; // samples 0..9 and 10..19, 3 bits each
         const uint32_t sp = stage + (j & (kChunkSlices - 1)) * (kSliceLen * 2);
         if (__all_sync(kFull, len == kSliceLen || !active)) { // steady state (an idle half computes on zeros)
-            candidate_step(l, lds_s16(sp), recip, lut_lane, err, pen, codes_a);
+            candidate_step(l, lds_s16(sp), recip, lut_lane, err, pen, codes_a, zero);
             first_err = (uint32_t)err; // error^2 of one sample fits 32 bits
             first_pen = pen;
 #pragma unroll
-            for (int i = 1; i < 10; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_a);
+            for (int i = 1; i < 10; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_a, zero);
 #pragma unroll
-            for (int i = 10; i < 20; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_b);
+            for (int i = 10; i < 20; ++i) candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, codes_b, zero);
         } else { // a partial last slice somewhere in the warp
 #pragma unroll 1
             for (uint32_t i = 0; i < kSliceLen; ++i) {
                 if (i < len) {
-                    candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, i < 10 ? codes_a : codes_b);
+                    candidate_step(l, lds_s16(sp + i * 2), recip, lut_lane, err, pen, i < 10 ? codes_a : codes_b, zero);
                     if (i == 0) {
                         first_err = (uint32_t)err;
                         first_pen = pen;
@@ -274,7 +276,7 @@ cudaError_t launch_encode(const int16_t *d_pcm, uint8_t *d_out, const EncJob *d_
     if (n_chains == 0) return cudaSuccess;
     const uint32_t warps = (n_chains + 1) / 2;
     const uint32_t blocks = (warps + kEncWarps - 1) / kEncWarps;
-    encode_kernel<<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms);
+    encode_kernel<<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms, 0);
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
