@@ -1,0 +1,35 @@
+// Builds libqoa_b200 from the CUDA sources with nvcc (sm_100a only) and links it statically.
+// Not compiled in the development image (no rustc); mirrors qoaudio_b200/csrc/Makefile.
+use std::{env, path::PathBuf, process::Command};
+
+fn main() {
+    let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../..");
+    let csrc = root.join("qoaudio_b200/csrc");
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
+    let mut objs = vec![];
+    for src in ["qoa_api.cu", "qoa_decode.cu", "qoa_encode.cu", "qoa_gen.cu"] {
+        let obj = out.join(src.replace(".cu", ".o"));
+        let ok = Command::new(&nvcc)
+            .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])
+            .arg(csrc.join(src))
+            .arg("-o")
+            .arg(&obj)
+            .status()
+            .expect("nvcc not found")
+            .success();
+        assert!(ok, "nvcc failed on {src}");
+        objs.push(obj);
+        println!("cargo:rerun-if-changed={}", csrc.join(src).display());
+    }
+    let lib = out.join("libqoa_b200.a");
+    assert!(Command::new("ar").arg("crs").arg(&lib).args(&objs).status().unwrap().success());
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-lib=static=qoa_b200");
+    println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
+    println!("cargo:rustc-link-lib=static=cudart_static");
+    println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=dl");
+    println!("cargo:rustc-link-lib=dylib=rt");
+    println!("cargo:rerun-if-changed={}", root.join("include/qoa_b200.h").display());
+}
