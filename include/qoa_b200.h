@@ -84,6 +84,7 @@ typedef struct {
 } qoa_b200_stream_info;
 #define QOA_B200_INFO_UNIFORM_CH 1u  /* every indexed frame has `max_channels` channels */
 #define QOA_B200_INFO_ALIGNED16 2u   /* every indexed frame starts 16-byte aligned in the stream's PCM output */
+#define QOA_B200_INFO_REGULAR 4u     /* conforming layout (all frames but the last hold 5120 samples): indexed in closed form */
 
 /* FrameHeader, src/lib.rs:773-781 */
 typedef struct {

@@ -545,7 +545,8 @@ struct qoa_b200_decode_plan {
 
 namespace {
 
-int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in_off, const size_t *len, cudaStream_t s)
+int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in_off, const size_t *len, cudaStream_t s,
+               int speculate = 1)
 {
     const size_t n = plan->n;
     Scratch sc(ctx);
@@ -553,24 +554,31 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     uint64_t *d_len = sc.get<uint64_t>(n);
     uint64_t *d_fbase = sc.get<uint64_t>(n + 1);
     qoa_b200_stream_info *d_info = sc.get<qoa_b200_stream_info>(n);
-    if (!d_off || !d_len || !d_fbase || !d_info) {
+    int *d_bad = sc.get<int>(4);
+    if (!d_off || !d_len || !d_fbase || !d_info || !d_bad) {
         ctx->err = "out of device memory (index tables)";
         return QOA_B200_E_NOMEM;
     }
     std::vector<uint64_t> len64(len, len + n);
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_len, len64.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CHECK_CUDA(ctx, launch_index_count(plan->d_arena, d_off, d_len, n, plan->mode, d_info, s));
+    CHECK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+    CHECK_CUDA(ctx, launch_index_count(plan->d_arena, d_off, d_len, n, plan->mode, speculate, d_info, s));
     ctx->launches += 1;
     plan->info.resize(n);
     CHECK_CUDA(ctx, cudaMemcpyAsync(plan->info.data(), d_info, n * sizeof(qoa_b200_stream_info), cudaMemcpyDeviceToHost, s));
     CHECK_CUDA(ctx, cudaStreamSynchronize(s));
     plan->frame_base.assign(n + 1, 0);
-    uint32_t max_ch = 0;
+    uint32_t max_ch = 0, max_regular_frames = 0;
+    size_t n_regular = 0;
     bool stereo = true;
     for (size_t i = 0; i < n; ++i) {
         const auto &inf = plan->info[i];
         plan->frame_base[i + 1] = plan->frame_base[i] + inf.index_frames;
+        if (inf.flags & QOA_B200_INFO_REGULAR) {
+            ++n_regular;
+            max_regular_frames = std::max(max_regular_frames, inf.index_frames);
+        }
         if (inf.index_frames) {
             max_ch = std::max(max_ch, inf.max_channels);
             if (inf.max_channels != 2 || !(inf.flags & QOA_B200_INFO_UNIFORM_CH) || !(inf.flags & QOA_B200_INFO_ALIGNED16))
@@ -581,14 +589,29 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     plan->max_ch = max_ch;
     plan->all_stereo = stereo && plan->n_frames > 0;
     if (plan->n_frames) {
-        plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
+        if (!plan->d_recs) plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
         if (!plan->d_recs) {
             ctx->err = "out of device memory (frame index)";
             return QOA_B200_E_NOMEM;
         }
         CHECK_CUDA(ctx, cudaMemcpyAsync(d_fbase, plan->frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-        CHECK_CUDA(ctx, launch_index_fill(plan->d_arena, d_off, d_len, n, plan->mode, d_fbase, plan->d_recs, s));
-        ctx->launches += 1;
+        if (n_regular < n) {
+            CHECK_CUDA(ctx, launch_index_fill(plan->d_arena, d_off, d_len, n, plan->mode, d_info, d_fbase, plan->d_recs, s));
+            ctx->launches += 1;
+        }
+        if (n_regular) {
+            CHECK_CUDA(ctx, launch_index_fill_regular(plan->d_arena, d_off, n, max_regular_frames, d_info, d_fbase,
+                                                      plan->d_recs, d_bad, s));
+            ctx->launches += 1;
+            int bad = 0;
+            CHECK_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CHECK_CUDA(ctx, cudaStreamSynchronize(s));
+            if (bad) { // some frame header is not the closed-form one: index the batch by walking
+                ctx->release(plan->d_recs);
+                plan->d_recs = nullptr;
+                return plan_index(ctx, plan, in_off, len, s, 0);
+            }
+        }
     }
     return 0;
 }

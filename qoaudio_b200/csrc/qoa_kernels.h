@@ -10,13 +10,21 @@
 namespace qoa {
 
 // ---- decode --------------------------------------------------------------------------------------------------
-// Index pre-pass, pass 1: one thread per stream walks the frame headers (src/lib.rs:205-289 semantics) and fills
-// d_info[i] (info.index_frames = number of frames that go into the frame table).
+// Index pre-pass, pass 1: one thread per stream.  With `speculate`, a stream whose length and first frame header match
+// the closed-form layout of a conforming encoder is accepted as "regular" (QOA_B200_INFO_REGULAR) without walking;
+// every other stream is walked frame header by frame header (src/lib.rs:205-289 semantics).  Fills d_info[i]
+// (info.index_frames = number of frames that go into the frame table).
 cudaError_t launch_index_count(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
-                               int mode, qoa_b200_stream_info *d_info, cudaStream_t s);
-// Pass 2: same walk, writes FrameRec entries at d_recs[d_frame_base[i] + f].
+                               int mode, int speculate, qoa_b200_stream_info *d_info, cudaStream_t s);
+// Pass 2 for walked streams: same walk, writes FrameRec entries at d_recs[d_frame_base[i] + f].
 cudaError_t launch_index_fill(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
-                              int mode, const uint64_t *d_frame_base, FrameRec *d_recs, cudaStream_t s);
+                              int mode, const qoa_b200_stream_info *d_info, const uint64_t *d_frame_base,
+                              FrameRec *d_recs, cudaStream_t s);
+// Pass 2 for regular streams: one thread per frame verifies the header word and writes the FrameRec; *d_bad is set
+// if any header differs from the closed-form expectation (the caller then re-indexes without speculation).
+cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_in_off, size_t n, uint32_t max_frames,
+                                      const qoa_b200_stream_info *d_info, const uint64_t *d_frame_base,
+                                      FrameRec *d_recs, int *d_bad, cudaStream_t s);
 // Frame-parallel decode.  max_ch = largest channel count of any frame in the table; d_out_base[stream] = i16 element
 // offset of the stream's output in d_out (UINT64_MAX = do not write this stream); out_bytes = extent of the output arena
 // that the batch may touch (upper bound of any written byte offset).

@@ -280,6 +280,29 @@ def test_malformed_headers(eng):
     check_decode_batch(eng, cases, 1)
 
 
+def test_speculative_index_falls_back_to_walking(eng):
+    """Conforming-length files take the closed-form index; a single foreign frame header anywhere in the batch must
+    send the batch back to the serial walk and give exactly the walk's (= the reference's) result."""
+    good = [ob.encode_all(signals.synth_pcm(6, i, c, n), c, 44100, n)[1] for i, (c, n) in
+            enumerate([(2, 5120 * 3 + 77), (1, 5120 * 2), (2, 25), (3, 5121)])]
+    fsz = 8 + 32 + 2048 * 2
+    cases = list(good)
+    for pos, patch in ((8 + fsz + 1, 0x12), (8 + 2 * fsz + 5, 0x99), (8 + fsz, 0x03), (8 + 3 * fsz + 7, 0x00), (8 + fsz + 4, 0xff)):
+        b = bytearray(good[0])
+        b[pos] = patch  # rate / nspc / channels / frame_size of an interior or the last frame header
+        cases.append(bytes(b))
+    b = bytearray(good[0])
+    b[8 + fsz + 8 + 3] ^= 0x55  # LMS bytes are payload, not layout: still regular, different samples
+    cases.append(bytes(b))
+    for mode in (0, 1):
+        check_decode_batch(eng, cases, mode)
+        check_decode_batch(eng, good, mode)
+    infos, _ = eng.decode_batch(good, 0)
+    assert all(i["flags"] & 4 for i in infos)          # QOA_B200_INFO_REGULAR
+    infos, _ = eng.decode_batch(cases, 0)
+    assert not any(i["flags"] & 4 for i in infos)      # the whole batch was walked
+
+
 def test_streaming_decode_frames(eng, fixture_bytes, N):
     """src/lib.rs:1034-1066: new_streaming + decode_frame on the first two fixture frames."""
     pos = 8
