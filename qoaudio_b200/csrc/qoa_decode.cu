@@ -306,16 +306,17 @@ cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_
 // ================================================================================================================
 
 // Dequant LUT in shared memory: entry (sf*8 + code) holds {dequantized, dequantized >> 4} (the residual and the LMS
-// delta of update(), src/lib.rs:822) and is replicated per lane so that every lane reads its own bank pair:
-// lane L's copy of entry e lives at byte e*256 + L*8 (32 KiB; an LDS.64 per half-warp is conflict-free).
-constexpr int kLutBytes = 128 * 32 * 8;
-constexpr uint32_t kLutAlign = 2048; // bits 8..10 of the base must be zero: code offsets are OR-ed into the address
+// delta of update(), src/lib.rs:822) and is replicated 16 times so that the 16 lanes of a half-warp (one wavefront of
+// a 64-bit shared load) read 16 distinct bank pairs: copy (L & 15) of entry e lives at byte e*128 + (L & 15)*8
+// (16 KiB, conflict-free).
+constexpr int kLutBytes = 128 * 16 * 8;
+constexpr uint32_t kLutAlign = 1024; // bits 7..9 of the base must be zero: code offsets are OR-ed into the address
 
 __device__ __forceinline__ void fill_lut(uint8_t *lut)
 {
     int2 *v = reinterpret_cast<int2 *>(lut);
-    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
-        const int dq = c_dequant[i >> 5];
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+        const int dq = c_dequant[i >> 4];
         v[i] = make_int2(dq, dq >> 4);
     }
     __syncthreads();
@@ -350,13 +351,13 @@ __device__ __forceinline__ void load_lms(Chain &c, const uint8_t *p)
     c.s3 = sign_pm1(c.h3);
 }
 
-// Byte offset (code * 256) of sample I's 3-bit code inside the lane-replicated LUT.
+// Byte offset (code * 128) of sample I's 3-bit code inside the replicated LUT.
 // Slice word layout (:303, :308): sf in bits 63..60, sample i's code in bits 59-3i .. 57-3i.
 template <int I>
 __device__ __forceinline__ uint32_t code_off(uint32_t hi, uint32_t lo)
 {
     constexpr int pos = 57 - 3 * I; // LSB of the code within the 64-bit word
-    constexpr int sh = pos - 8;     // shift that brings the code to bits 10..8
+    constexpr int sh = pos - 7;     // shift that brings the code to bits 9..7
     uint32_t v;
     if constexpr (sh >= 32)
         v = hi >> (sh - 32);
@@ -366,7 +367,7 @@ __device__ __forceinline__ uint32_t code_off(uint32_t hi, uint32_t lo)
         v = lo;
     else
         v = lo << (-sh);
-    return v & 0x700u;
+    return v & 0x380u;
 }
 
 __device__ __forceinline__ int2 lds_v2(uint32_t addr)
@@ -377,7 +378,7 @@ __device__ __forceinline__ int2 lds_v2(uint32_t addr)
 }
 
 // One sample of one channel (:306-317).  `row` = shared address of the lane's LUT entries for this slice's
-// scalefactor (2 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
+// scalefactor (1 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
 template <int I>
 __device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
 {
@@ -470,8 +471,9 @@ struct SingleLoop<20> {
 //     2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = S*20 words x 32 rows of a tensor map that
 //     views the output arena as rows of 20480 bytes) — no copy-out instructions at all;
 //   * everything else (warps that straddle two streams, short last frames, partial slices, the group that crosses a
-//     20480-byte row of the arena-wide map): one 1-D bulk copy per lane (cp.async.bulk; the hardware takes uniform
-//     operands, so this path serialises over the lanes — it is the fallback, not the steady state).
+//     20480-byte row of the arena-wide map; ~8 % of the groups): every lane copies its own row with 16-byte
+//     shared loads / global stores.  (Per-lane cp.async.bulk copies were measured first: UBLKCP takes uniform
+//     operands, so the compiler serialises it over the 32 lanes — ~480 instructions per group.)
 // S is odd so that the row pitch (S*80 bytes) is an odd multiple of 16: the 128-bit staging stores of a quarter-warp
 // then hit eight distinct bank groups.  NB tiles per warp form a ring.
 // Slice words arrive through a per-lane ring of four 16-byte vectors filled by cp.async two to three slices ahead
@@ -511,7 +513,7 @@ __device__ __forceinline__ void bulk_wait_read()
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -531,7 +533,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 }
 
 template <int S, int NB, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
 decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                      const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
                      const __grid_constant__ CUtensorMap out_map, int use_map)
@@ -592,7 +594,7 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
         b = a;
     }
     uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
-    const uint32_t lane_row = smem_u32(smem) + lane * 8;
+    const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
     const uint32_t warp_tiles = smem_u32(smem + kLutBytes) + (threadIdx.x >> 5) * Cfg::kWarpBytes;
 
     uint32_t ring = 0;   // tile of the ring being filled
@@ -616,8 +618,8 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
             const uint32_t a_hi = ra.x, a_lo = ra.y, b_hi = rb.x, b_lo = rb.y;
             const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
             const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
-            const uint32_t row_a = lane_row + (wa.x >> 28) * 2048; // sf = top nibble (:303)
-            const uint32_t row_b = lane_row + (wb.x >> 28) * 2048;
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
             uint32_t o[20];
             PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
             const uint32_t dst_s = row + in_row * 80;
@@ -633,12 +635,17 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
             if (whole) { // every lane staged S full slices: one tensor store for the warp
                 if (lane == 0) tensor_store_2d(&out_map, tile, map_c0, map_c1);
             } else if (first < nsamp) {
-                // Samples past nsamp (partial last slice, :320-325) are not emitted.
+                // Irregular warp or group: every lane copies its own row with 16-byte loads/stores.  Samples past nsamp
+                // (partial last slice, :320-325) are not emitted.
                 const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * 4;
-                const uint32_t bulk = bytes & ~15u;
                 uint8_t *dst = op + (uint64_t)first * 4;
-                if (bulk) bulk_store_s2g(dst, row, bulk);
-                for (uint32_t t = bulk; t < bytes; t += 4) { // 1..3 trailing (L, R) words when nsamp % 4 != 0
+                uint32_t t = 0;
+                for (; t + 16 <= bytes; t += 16) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(row + t));
+                    *reinterpret_cast<uint4 *>(dst + t) = v;
+                }
+                for (; t < bytes; t += 4) { // 1..3 trailing (L, R) words when nsamp % 4 != 0
                     uint32_t v;
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
                     *reinterpret_cast<uint32_t *>(dst + t) = v;
@@ -718,11 +725,11 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     const uint8_t *sp = fp + 8 + 16 * ch + 8 * c;
     const uint32_t ngroups = (nsamp + kSliceLen - 1) / kSliceLen;
     int16_t *op = out + ob + rec.out_rel + c;
-    const uint32_t lane_row = smem_u32(lut) + (threadIdx.x & 31) * 8;
+    const uint32_t lane_row = smem_u32(lut) + (threadIdx.x & 15) * 8;
 
     for (uint32_t k = 0; k < ngroups; ++k) {
         const uint2 wa = ldg_be64(sp + (uint64_t)k * ch * 8);
-        const uint32_t row_a = lane_row + (wa.x >> 28) * 2048;
+        const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
         int16_t o[20];
         SingleLoop<0>::run(a, row_a, wa, o);
         const uint32_t base = k * kSliceLen;
@@ -770,16 +777,14 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
             variant = v ? atoi(v) : 0;
         }
         switch (variant) {
-        case 1: e = launch_stereo<3, 1, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 2: e = launch_stereo<3, 1, 448>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 3: e = launch_stereo<3, 1, 480>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 4: e = launch_stereo<3, 1, 544>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 5: e = launch_stereo<3, 1, 576>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 6: e = launch_stereo<5, 1, 384>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 7: e = launch_stereo<5, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 8: e = launch_stereo<1, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 9: e = launch_stereo<1, 2, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        default: e = launch_stereo<3, 1, 512>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 1: e = launch_stereo<3, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 2: e = launch_stereo<3, 1, 192>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 3: e = launch_stereo<3, 1, 640>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 4: e = launch_stereo<3, 1, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 5: e = launch_stereo<3, 1, 128>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 6: e = launch_stereo<5, 1, 224>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 7: e = launch_stereo<3, 1, 704>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        default: e = launch_stereo<3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         }
     } else {
         const uint64_t n_units = n_frames * max_ch;
