@@ -38,6 +38,11 @@ struct qoa_b200_ctx {
     std::vector<PoolBlock> pool;
     cudaStream_t last_stream = nullptr;
     bool used = false;
+    // pipelined host calls: several internal streams are in flight at once, so scratch blocks are only returned to
+    // the pool when the whole call has drained
+    bool pipelining = false;
+    std::vector<void *> deferred;
+    cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
 
     void *alloc(size_t bytes)
     {
@@ -71,6 +76,10 @@ struct qoa_b200_ctx {
     void release(void *p)
     {
         if (!p) return;
+        if (pipelining) {
+            deferred.push_back(p);
+            return;
+        }
         for (auto &b : pool)
             if (b.ptr == p) {
                 b.free = true;
@@ -80,6 +89,7 @@ struct qoa_b200_ctx {
     // Scratch blocks are recycled without waiting: safe as long as work is enqueued on one stream at a time.
     void enter(cudaStream_t s)
     {
+        if (pipelining) return;
         if (used && s != last_stream) cudaStreamSynchronize(last_stream);
         last_stream = s;
         used = true;
@@ -159,6 +169,8 @@ void qoa_b200_ctx_destroy(qoa_b200_ctx *ctx)
     cudaDeviceSynchronize();
     for (auto &b : ctx->pool)
         if (b.ptr) cudaFree(b.ptr);
+    for (auto &ps : ctx->pipe_streams)
+        if (ps) cudaStreamDestroy(ps);
     delete ctx;
 }
 
@@ -656,8 +668,8 @@ extern "C" int qoa_b200_decode_plan_create_dev(qoa_b200_ctx *ctx, const uint8_t 
     return 0;
 }
 
-extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
-                                           int mode, qoa_b200_decode_plan **out)
+static int plan_create_host(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n, int mode,
+                            cudaStream_t s, qoa_b200_decode_plan **out)
 {
     if (!ctx || !out) return QOA_B200_E_ARG;
     *out = nullptr;
@@ -666,7 +678,6 @@ extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *con
         return QOA_B200_E_ARG;
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = nullptr;
     ctx->enter(s);
     std::vector<uint64_t> off(n, 0);
     uint64_t total = 0;
@@ -696,6 +707,12 @@ extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *con
     }
     (*out)->owned_arena = arena;
     return 0;
+}
+
+extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
+                                           int mode, qoa_b200_decode_plan **out)
+{
+    return plan_create_host(ctx, qoa, len, n, mode, nullptr, out);
 }
 
 extern "C" void qoa_b200_decode_plan_destroy(qoa_b200_decode_plan *plan)
@@ -781,8 +798,9 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     return 0;
 }
 
-extern "C" int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *const *out, const size_t *out_cap,
-                                        int32_t *status)
+// Decode + D2H on stream s.  With sync == false the copies are left in flight (the caller drains the stream).
+static int plan_run_host(qoa_b200_decode_plan *plan, int16_t *const *out, const size_t *out_cap, int32_t *status,
+                         cudaStream_t s, bool sync)
 {
     if (!plan) return QOA_B200_E_ARG;
     qoa_b200_ctx *ctx = plan->ctx;
@@ -793,7 +811,6 @@ extern "C" int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *con
         return QOA_B200_E_ARG;
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->last_stream;
     std::vector<uint64_t> off(n, 0);
     uint64_t total = 0;
     for (size_t i = 0; i < n; ++i) {
@@ -817,27 +834,81 @@ extern "C" int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *con
                 rc = QOA_B200_E_CUDA;
             }
         }
-        cudaError_t e = cudaStreamSynchronize(s);
+        cudaError_t e = sync ? cudaStreamSynchronize(s) : cudaSuccess;
         if (e != cudaSuccess && rc == 0) {
             ctx->err = std::string("decode: ") + cudaGetErrorString(e);
             cudaGetLastError();
             rc = QOA_B200_E_CUDA;
         }
     }
-    ctx->release(d_out);
+    ctx->release(d_out); // deferred while pipelining
     return rc;
+}
+
+extern "C" int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *const *out, const size_t *out_cap,
+                                        int32_t *status)
+{
+    if (!plan) return QOA_B200_E_ARG;
+    return plan_run_host(plan, out, out_cap, status, plan->ctx->last_stream, true);
 }
 
 extern "C" int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
                                          int mode, int16_t *const *out, const size_t *out_cap,
                                          qoa_b200_stream_info *info, int32_t *status)
 {
-    qoa_b200_decode_plan *plan = nullptr;
-    int rc = qoa_b200_decode_plan_create(ctx, qoa, len, n, mode, &plan);
-    if (rc != 0) return rc;
-    if (info) qoa_b200_decode_plan_info(plan, info);
-    rc = qoa_b200_decode_plan_run(plan, out, out_cap, status);
-    qoa_b200_decode_plan_destroy(plan);
+    if (!ctx) return QOA_B200_E_ARG;
+    if (n && (!qoa || !len)) {
+        ctx->err = "null argument";
+        return QOA_B200_E_ARG;
+    }
+    uint64_t total_in = 0;
+    for (size_t i = 0; i < n; ++i) total_in += len[i];
+    constexpr uint64_t kChunkBytes = 24ull << 20; // input bytes per pipeline stage (~5x that in PCM coming back)
+    if (n < 8 || total_in < 3 * kChunkBytes) { // small batch: one shot
+        qoa_b200_decode_plan *plan = nullptr;
+        int rc = qoa_b200_decode_plan_create(ctx, qoa, len, n, mode, &plan);
+        if (rc != 0) return rc;
+        if (info) qoa_b200_decode_plan_info(plan, info);
+        rc = qoa_b200_decode_plan_run(plan, out, out_cap, status);
+        qoa_b200_decode_plan_destroy(plan);
+        return rc;
+    }
+    // Large batch: software pipeline over chunks of streams on three internal streams, so that the H2D copy of chunk
+    // c + 1, the index + decode of chunk c and the D2H copy of chunk c - 1 overlap (PCIe is full duplex; the path is
+    // D2H-bound: 2 bytes out per 0.4 bytes in).
+    CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->used) CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->last_stream));
+    for (auto &ps : ctx->pipe_streams)
+        if (!ps) CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    ctx->pipelining = true;
+    std::vector<qoa_b200_decode_plan *> plans;
+    int rc = 0;
+    size_t b = 0;
+    for (int c = 0; b < n && rc == 0; ++c) {
+        size_t e = b;
+        uint64_t bytes = 0;
+        while (e < n && (e == b || bytes + len[e] <= kChunkBytes)) bytes += len[e++];
+        cudaStream_t s = ctx->pipe_streams[c % 3];
+        qoa_b200_decode_plan *plan = nullptr;
+        rc = plan_create_host(ctx, qoa + b, len + b, e - b, mode, s, &plan);
+        if (rc != 0) break;
+        plans.push_back(plan);
+        if (info) qoa_b200_decode_plan_info(plan, info + b);
+        rc = plan_run_host(plan, out + b, out_cap + b, status ? status + b : nullptr, s, false);
+        b = e;
+    }
+    for (auto &ps : ctx->pipe_streams) {
+        cudaError_t e = cudaStreamSynchronize(ps);
+        if (e != cudaSuccess && rc == 0) {
+            ctx->err = std::string("decode_all_batch: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            rc = QOA_B200_E_CUDA;
+        }
+    }
+    for (auto *p : plans) qoa_b200_decode_plan_destroy(p);
+    ctx->pipelining = false;
+    for (void *p : ctx->deferred) ctx->release(p);
+    ctx->deferred.clear();
     return rc;
 }
 

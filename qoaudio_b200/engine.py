@@ -127,6 +127,24 @@ class Engine:
         finally:
             plan.close()
 
+    def decode_all_batch(self, streams, caps, mode=N.DECODE_ALL):
+        """One-call host path (qoa_b200_decode_all_batch): large batches are pipelined over chunks of streams so that
+        H2D, decode and D2H overlap.  streams: list of np.uint8 arrays; caps: capacity (i16 values) per stream.
+        Returns (info structured array, status np.int32 array, list of np.int16 arrays of length caps[i])."""
+        n = len(streams)
+        bufs = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
+        outs = [np.empty(int(c), dtype=np.int16) for c in caps]
+        info = np.zeros(n, dtype=INFO_DTYPE)
+        status = np.zeros(n, dtype=np.int32)
+        k = _Keep()
+        rc = N.lib().qoa_b200_decode_all_batch(
+            self._h, k.arr([b.ctypes.data if b.size else None for b in bufs], C.c_void_p),
+            k.arr([b.size for b in bufs], C.c_size_t), n, mode,
+            k.arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p), k.arr([o.size for o in outs], C.c_size_t),
+            C.c_void_p(info.ctypes.data), C.c_void_p(status.ctypes.data))
+        N.check(self._h, rc, "qoa_b200_decode_all_batch")
+        return info, status, outs
+
     # ---- generators / microbenchmarks --------------------------------------------------------------------------
     def gen_pcm_dev(self, d_pcm, n_streams, first_stream, channels, samples, start, seed, kind="music", stream=0):
         rc = N.lib().qoa_b200_gen_pcm_dev(self._h, C.c_void_p(d_pcm), n_streams, first_stream, channels, samples, start,

@@ -392,3 +392,29 @@ def test_device_encode_chunked_equals_one_shot(eng):
     two = out2.cpu().numpy().reshape(n_streams, stride)[:, 8:size]
     assert np.array_equal(two, one[:, 8:])
     batch.close()
+
+
+def test_decode_all_batch_pipelined(eng):
+    """qoa_b200_decode_all_batch pipelines large host batches over chunks of streams on three CUDA streams; the
+    result must equal the one-shot plan path and the oracle, including failing streams in the middle of a chunk."""
+    import torch
+    ch, rate, n = 2, 44100, 5120 * 200 + 4080
+    size = ob.encoded_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    count = 96  # ~80 MB of input: above the pipelining threshold
+    t = torch.zeros(count * stride, dtype=torch.uint8, device="cuda")
+    eng.gen_qoa_dev(t.data_ptr(), stride, count, 0, ch, rate, n, 5)
+    torch.cuda.synchronize()
+    host = t.cpu().numpy()
+    streams = [host[i * stride:i * stride + size] for i in range(count)]
+    streams[7] = streams[7][:size - 1000]          # truncated: IoError, nothing written beyond what was decoded
+    streams[40] = np.frombuffer(b"nope" + bytes(60), dtype=np.uint8)
+    caps = [n * ch] * count
+    info, status, outs = eng.decode_all_batch(streams, caps)
+    for i in (0, 1, 7, 39, 40, 41, 95):
+        oi, opcm = ob.decode_all(streams[i].tobytes())
+        assert status[i] == oi["status"] and int(info["samples"][i]) == oi["samples"], i
+        assert np.array_equal(outs[i][:oi["samples"]], opcm), i
+    infos2, outs2 = eng.decode_batch([s.tobytes() for s in streams[:12]], 1)
+    for i in range(12):
+        assert np.array_equal(outs[i][:infos2[i]["samples"]], outs2[i])

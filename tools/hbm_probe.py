@@ -16,3 +16,9 @@ ms = t(lambda: a.zero_()); print(f"write-only fill : {2*n/ms/1e6:8.1f} GB/s")
 ms = t(lambda: a.fill_(7)); print(f"write-only fill7: {2*n/ms/1e6:8.1f} GB/s")
 ms = t(lambda: b.copy_(a)); print(f"copy (r+w)      : {4*n/ms/1e6:8.1f} GB/s")
 ms = t(lambda: torch.sum(a[: n // 2].view(torch.int32))); print(f"read-only sum   : {n/ms/1e6:8.1f} GB/s")
+
+# PCIe ceilings for the e2e path (pinned host memory)
+h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+d = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+ms = t(lambda: h.copy_(d, non_blocking=True)); print(f"D2H pinned 1 GiB : {(1<<30)/ms/1e6:8.1f} GB/s")
+ms = t(lambda: d.copy_(h, non_blocking=True)); print(f"H2D pinned 1 GiB : {(1<<30)/ms/1e6:8.1f} GB/s")
