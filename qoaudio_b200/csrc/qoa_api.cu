@@ -43,6 +43,33 @@ struct qoa_b200_ctx {
     bool pipelining = false;
     std::vector<void *> deferred;
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
+    // host-mapped (pinned) result slots the index kernels write directly: one region per pipeline stream
+    struct Mapped {
+        void *ptr = nullptr;
+        size_t size = 0;
+    } mapped[4];
+    void *mapped_get(int slot, size_t bytes)
+    {
+        Mapped &m = mapped[slot];
+        if (m.size < bytes) {
+            if (m.ptr) cudaFreeHost(m.ptr);
+            m.ptr = nullptr;
+            m.size = 0;
+            const size_t want = std::max<size_t>(bytes * 2, 1 << 16);
+            if (cudaHostAlloc(&m.ptr, want, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            m.size = want;
+        }
+        return m.ptr;
+    }
+    int slot_of(cudaStream_t s) const
+    {
+        for (int i = 0; i < 3; ++i)
+            if (pipelining && s == pipe_streams[i]) return i + 1;
+        return 0;
+    }
 
     void *alloc(size_t bytes)
     {
@@ -171,6 +198,8 @@ void qoa_b200_ctx_destroy(qoa_b200_ctx *ctx)
         if (b.ptr) cudaFree(b.ptr);
     for (auto &ps : ctx->pipe_streams)
         if (ps) cudaStreamDestroy(ps);
+    for (auto &m : ctx->mapped)
+        if (m.ptr) cudaFreeHost(m.ptr);
     delete ctx;
 }
 
@@ -566,20 +595,22 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     uint64_t *d_len = sc.get<uint64_t>(n);
     uint64_t *d_fbase = sc.get<uint64_t>(n + 1);
     qoa_b200_stream_info *d_info = sc.get<qoa_b200_stream_info>(n);
-    int *d_bad = sc.get<int>(4);
-    if (!d_off || !d_len || !d_fbase || !d_info || !d_bad) {
-        ctx->err = "out of device memory (index tables)";
+    // host-mapped results: [int bad flag (64 bytes reserved)] [n x stream_info]
+    uint8_t *mapped = static_cast<uint8_t *>(ctx->mapped_get(ctx->slot_of(s), 64 + n * sizeof(qoa_b200_stream_info)));
+    if (!d_off || !d_len || !d_fbase || !d_info || !mapped) {
+        ctx->err = "out of memory (index tables)";
         return QOA_B200_E_NOMEM;
     }
+    volatile int *h_bad = reinterpret_cast<volatile int *>(mapped);
+    qoa_b200_stream_info *h_info = reinterpret_cast<qoa_b200_stream_info *>(mapped + 64);
+    *h_bad = 0;
     std::vector<uint64_t> len64(len, len + n);
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_off, in_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_len, len64.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CHECK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), s));
-    CHECK_CUDA(ctx, launch_index_count(plan->d_arena, d_off, d_len, n, plan->mode, speculate, d_info, s));
+    CHECK_CUDA(ctx, launch_index_count(plan->d_arena, d_off, d_len, n, plan->mode, speculate, d_info, h_info, s));
     ctx->launches += 1;
-    plan->info.resize(n);
-    CHECK_CUDA(ctx, cudaMemcpyAsync(plan->info.data(), d_info, n * sizeof(qoa_b200_stream_info), cudaMemcpyDeviceToHost, s));
     CHECK_CUDA(ctx, cudaStreamSynchronize(s));
+    plan->info.assign(h_info, h_info + n);
     plan->frame_base.assign(n + 1, 0);
     uint32_t max_ch = 0, max_regular_frames = 0;
     size_t n_regular = 0;
@@ -613,12 +644,10 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
         }
         if (n_regular) {
             CHECK_CUDA(ctx, launch_index_fill_regular(plan->d_arena, d_off, n, max_regular_frames, d_info, d_fbase,
-                                                      plan->d_recs, d_bad, s));
+                                                      plan->d_recs, const_cast<int *>(h_bad), s));
             ctx->launches += 1;
-            int bad = 0;
-            CHECK_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
             CHECK_CUDA(ctx, cudaStreamSynchronize(s));
-            if (bad) { // some frame header is not the closed-form one: index the batch by walking
+            if (*h_bad) { // some frame header is not the closed-form one: index the batch by walking
                 ctx->release(plan->d_recs);
                 plan->d_recs = nullptr;
                 return plan_index(ctx, plan, in_off, len, s, 0);

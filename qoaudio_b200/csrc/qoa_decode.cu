@@ -215,14 +215,18 @@ __device__ bool probe_regular(const uint8_t *p, uint64_t len, qoa_b200_stream_in
     return true;
 }
 
+// `host_info` is a host-mapped (pinned) mirror of the table: the host needs the per-stream results to size the frame
+// index, and reading them through mapped memory keeps the copy engines — busy with payload copies in the pipelined
+// host path — out of the dependency chain.
 __global__ void index_count_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ in_off,
                                    const uint64_t *__restrict__ in_len, uint32_t n, int mode, int speculate,
-                                   qoa_b200_stream_info *__restrict__ info)
+                                   qoa_b200_stream_info *__restrict__ info, qoa_b200_stream_info *__restrict__ host_info)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (speculate && mode != QOA_B200_DECODE_FRAMES && probe_regular(arena + in_off[i], in_len[i], info + i)) return;
-    walk_stream<false>(arena, in_off[i], in_len[i], mode, i, nullptr, info + i);
+    if (!(speculate && mode != QOA_B200_DECODE_FRAMES && probe_regular(arena + in_off[i], in_len[i], info + i)))
+        walk_stream<false>(arena, in_off[i], in_len[i], mode, i, nullptr, info + i);
+    host_info[i] = info[i];
 }
 
 __global__ void index_fill_kernel(const uint8_t *__restrict__ arena, const uint64_t *__restrict__ in_off,
@@ -251,7 +255,7 @@ __global__ void index_fill_regular_kernel(const uint8_t *__restrict__ arena, con
         const uint64_t pos = 8 + (uint64_t)f * full;
         const uint2 h = ldg_be64(arena + in_off[i] + pos);
         const uint2 e = expected_header(ch, rate, frame_len);
-        if (h.x != e.x || h.y != e.y) atomicOr(bad, 1);
+        if (h.x != e.x || h.y != e.y) *reinterpret_cast<volatile int *>(bad) = 1; // host-mapped flag; every writer stores 1
         FrameRec r;
         r.in_off = in_off[i] + pos;
         r.out_rel = (uint64_t)f * kFrameLen * ch;
@@ -266,12 +270,13 @@ __global__ void index_fill_regular_kernel(const uint8_t *__restrict__ arena, con
 }
 
 cudaError_t launch_index_count(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
-                               int mode, int speculate, qoa_b200_stream_info *d_info, cudaStream_t s)
+                               int mode, int speculate, qoa_b200_stream_info *d_info, qoa_b200_stream_info *h_info,
+                               cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;
     const int block = 32; // one dependent-load chain per thread: spread the streams over as many SMs as possible
     index_count_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(d_arena, d_in_off, d_in_len, (uint32_t)n,
-                                                                             mode, speculate, d_info);
+                                                                             mode, speculate, d_info, h_info);
     return cudaGetLastError();
 }
 

@@ -14,14 +14,17 @@ namespace qoa {
 // the closed-form layout of a conforming encoder is accepted as "regular" (QOA_B200_INFO_REGULAR) without walking;
 // every other stream is walked frame header by frame header (src/lib.rs:205-289 semantics).  Fills d_info[i]
 // (info.index_frames = number of frames that go into the frame table).
+// h_info is a host-mapped (pinned) mirror of d_info that the kernel also writes.
 cudaError_t launch_index_count(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
-                               int mode, int speculate, qoa_b200_stream_info *d_info, cudaStream_t s);
+                               int mode, int speculate, qoa_b200_stream_info *d_info, qoa_b200_stream_info *h_info,
+                               cudaStream_t s);
 // Pass 2 for walked streams: same walk, writes FrameRec entries at d_recs[d_frame_base[i] + f].
 cudaError_t launch_index_fill(const uint8_t *d_arena, const uint64_t *d_in_off, const uint64_t *d_in_len, size_t n,
                               int mode, const qoa_b200_stream_info *d_info, const uint64_t *d_frame_base,
                               FrameRec *d_recs, cudaStream_t s);
 // Pass 2 for regular streams: one thread per frame verifies the header word and writes the FrameRec; *d_bad is set
-// if any header differs from the closed-form expectation (the caller then re-indexes without speculation).
+// (a host-mapped int) if any header differs from the closed-form expectation (the caller then re-indexes without
+// speculation).
 cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_in_off, size_t n, uint32_t max_frames,
                                       const qoa_b200_stream_info *d_info, const uint64_t *d_frame_base,
                                       FrameRec *d_recs, int *d_bad, cudaStream_t s);
