@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--no-encode", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -353,6 +354,49 @@ def main():
         batch.close()
         del epcm, eout
 
+    # ---------------------------------------------------------------- configs[1]: ONE 54 s stereo stream --------
+    # Latency-bound by construction (encode = one warp, decode = 466 threads): reported, not tuned for.
+    single = None
+    if rank == 0 and not args.no_single:
+        SN, SCH, SRATE = 2381400, 2, 44100
+        spcm = torch.empty(SN * SCH, dtype=torch.int16, device=dev)
+        eng.gen_pcm_dev(spcm.data_ptr(), 1, 0, SCH, SN, 0, 1, "music", stream)
+        ssize = enc_size(SCH, SN)
+        sq = torch.zeros((ssize + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+        sout = torch.empty(SN * SCH, dtype=torch.int16, device=dev)
+        t_enc, t_dec = [], []
+        for it in range(3):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            st, ln = eng.encode_all_batch_dev([(SCH, SRATE, SN)], spcm.data_ptr(), [0], [SN * SCH], sq.data_ptr(), [0],
+                                              [sq.numel()], stream)
+            b.record()
+            plan = eng.decode_plan_dev(sq.data_ptr(), [0], [ssize], q._native.DECODE_ALL, stream)
+            plan.run_dev(sout.data_ptr(), [0], [SN * SCH], stream)
+            c.record()
+            torch.cuda.synchronize()
+            plan.close()
+            assert st == [0] and ln == [ssize]
+            if it:
+                t_enc.append(a.elapsed_time(b))
+                t_dec.append(b.elapsed_time(c))
+        single = {"workload": "single synthetic 54 s stereo 44.1 kHz stream (BASELINE.json configs[1])",
+                  "encode_ms": min(t_enc), "decode_ms": min(t_dec),
+                  "encode_msamples_s": SN * SCH / min(t_enc) / 1e3, "decode_msamples_s": SN * SCH / min(t_dec) / 1e3}
+        if not args.no_cpu:
+            from oracle import binding as ob
+            hp = spcm.cpu().numpy()
+            t0 = time.perf_counter()
+            _, ref = ob.encode_all(hp, SCH, SRATE, SN)
+            t1 = time.perf_counter()
+            _, rpcm = ob.decode_all(ref)
+            t2 = time.perf_counter()
+            assert sq[:ssize].cpu().numpy().tobytes() == ref, "single-stream encode differs from the oracle"
+            assert (sout.cpu().numpy() == rpcm).all(), "single-stream decode differs from the oracle"
+            single.update({"cpu_encode_ms": (t1 - t0) * 1e3, "cpu_decode_ms": (t2 - t1) * 1e3,
+                           "parity": "bit-exact vs oracle"})
+        del spcm, sq, sout
+
     if rank != 0:
         grp.close()
         return
@@ -386,7 +430,7 @@ def main():
                      "note": "decode writes 8.5x what it reads; write-only HBM measured at 3.94 TB/s on this part "
                              "(tools/hbm_probe.py), i.e. a workload ceiling of ~0.72 of the copy peak"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
-        "encode": encode,
+        "encode": encode, "single_stream": single,
     }
     print(json.dumps(line))
     grp.close()
