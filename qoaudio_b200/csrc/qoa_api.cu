@@ -579,7 +579,7 @@ struct qoa_b200_decode_plan {
     FrameRec *d_recs = nullptr;
     uint64_t n_frames = 0;
     uint32_t max_ch = 0;
-    bool all_stereo = false;
+    uint32_t uniform_ch = 0; // 1 / 2: every indexed frame is mono / stereo and 16-byte aligned in the output
     std::vector<qoa_b200_stream_info> info;
     std::vector<uint64_t> frame_base; // n + 1
 };
@@ -614,7 +614,8 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     plan->frame_base.assign(n + 1, 0);
     uint32_t max_ch = 0, max_regular_frames = 0;
     size_t n_regular = 0;
-    bool stereo = true;
+    bool uniform = true;
+    uint32_t first_ch = 0;
     for (size_t i = 0; i < n; ++i) {
         const auto &inf = plan->info[i];
         plan->frame_base[i + 1] = plan->frame_base[i] + inf.index_frames;
@@ -624,13 +625,14 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
         }
         if (inf.index_frames) {
             max_ch = std::max(max_ch, inf.max_channels);
-            if (inf.max_channels != 2 || !(inf.flags & QOA_B200_INFO_UNIFORM_CH) || !(inf.flags & QOA_B200_INFO_ALIGNED16))
-                stereo = false;
+            if (!first_ch) first_ch = inf.max_channels;
+            if (inf.max_channels != first_ch || !(inf.flags & QOA_B200_INFO_UNIFORM_CH) || !(inf.flags & QOA_B200_INFO_ALIGNED16))
+                uniform = false;
         }
     }
     plan->n_frames = plan->frame_base[n];
     plan->max_ch = max_ch;
-    plan->all_stereo = stereo && plan->n_frames > 0;
+    plan->uniform_ch = (uniform && plan->n_frames > 0 && (first_ch == 1 || first_ch == 2)) ? first_ch : 0;
     if (plan->n_frames) {
         if (!plan->d_recs) plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
         if (!plan->d_recs) {
@@ -821,7 +823,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     }
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_base, base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
     int nl = 0;
-    CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs, plan->n_frames, plan->max_ch, plan->all_stereo && aligned,
+    CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs, plan->n_frames, plan->max_ch, aligned ? plan->uniform_ch : 0u,
                                   d_base, d_out, out_bytes, s, &nl));
     ctx->launches += nl;
     return 0;

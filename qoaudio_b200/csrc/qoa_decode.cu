@@ -463,46 +463,44 @@ struct SingleLoop<20> {
     static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, int16_t *) {}
 };
 
-// ---- stereo fast path ------------------------------------------------------------------------------------------
-// One thread = one frame, both channels (two independent LMS chains = ILP 2; (L, R) pairs pack into one 32-bit word).
-// Requirements (checked by the host from the index flags): every frame has 2 channels and starts 16-byte aligned in
+// ---- fast path for uniform mono / stereo batches ---------------------------------------------------------------
+// One thread = one frame, all of its channels: for stereo two independent LMS chains (ILP 2; an (L, R) pair packs into
+// one 32-bit word), for mono one chain (two consecutive samples per word).
+// Requirements (checked by the host from the index flags): every frame has CH channels and starts 16-byte aligned in
 // the PCM output.
 //
-// Memory path.  Lanes of a warp own different frames (4136 B apart in the input, 20480 B apart in the output), so
-// direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages S slices
-// (S * 80 B of interleaved PCM) in its own row of a per-warp shared-memory tile [32 lanes][S * 80 B] and the tile goes
-// to global memory through the TMA engine:
-//   * regular warps (32 consecutive full frames of one stream, i.e. rows exactly 20480 B apart in the output): ONE
-//     2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = S*20 words x 32 rows of a tensor map that
-//     views the output arena as rows of 20480 bytes) — no copy-out instructions at all;
+// Memory path.  Lanes of a warp own different frames (4136 B apart in the input, 20480 B apart in the output for
+// stereo), so direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages
+// S slices (240 B of PCM: S = 3 stereo, S = 6 mono) in its own row of a per-warp shared-memory tile [32 lanes][240 B]
+// and the tile goes to global memory through the TMA engine:
+//   * regular warps (32 consecutive full frames of one stream, i.e. rows exactly one frame of PCM apart in the
+//     output): ONE 2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = 60 words x 32 rows of a tensor
+//     map that views the output arena as rows of one frame of PCM) — no copy-out instructions at all;
 //   * everything else (warps that straddle two streams, short last frames, partial slices, the group that crosses a
-//     20480-byte row of the arena-wide map; ~8 % of the groups): every lane copies its own row with 16-byte
-//     shared loads / global stores.  (Per-lane cp.async.bulk copies were measured first: UBLKCP takes uniform
-//     operands, so the compiler serialises it over the 32 lanes — ~480 instructions per group.)
-// S is odd so that the row pitch (S*80 bytes) is an odd multiple of 16: the 128-bit staging stores of a quarter-warp
-// then hit eight distinct bank groups.  NB tiles per warp form a ring.
+//     row of the arena-wide map; ~8 % of the groups): every lane copies its own row with 16-byte shared loads /
+//     global stores.  (Per-lane cp.async.bulk copies were measured first: UBLKCP takes uniform operands, so the
+//     compiler serialises it over the 32 lanes — ~480 instructions per group.)
+// The row pitch (240 bytes) is an odd multiple of 16: the 128-bit staging stores of a quarter-warp hit eight distinct
+// bank groups.  NB tiles per warp form a ring.
 // Slice words arrive through a per-lane ring of four 16-byte vectors filled by cp.async two to three slices ahead
-// of use (frames are only 8-byte aligned: a slice pair is either one aligned vector or the upper half of one and the
-// lower half of the next — reading the ring with two 8-byte shared loads needs no alignment selects, and unlike a
+// of use (frames are only 8-byte aligned: a stereo slice pair is either one aligned vector or the upper half of one
+// and the lower half of the next — reading the ring with 8-byte shared loads needs no alignment selects, and unlike a
 // register prefetch the asynchronous copy never shares a scoreboard slot with the LUT loads).
-constexpr uint32_t kOutRowBytes = kFrameLen * 2 * 2; // PCM bytes of one full stereo frame = row pitch of the tensor map
-
-template <int S, int NB>
-struct StereoCfg {
-    static constexpr int kRowBytes = S * 80;             // PCM bytes one lane produces per group
-    static constexpr int kTileBytes = 32 * kRowBytes;    // one warp's tile
+template <int CH, int S, int NB>
+struct FastCfg {
+    static_assert(CH == 1 || CH == 2, "fast path: mono or stereo");
+    static constexpr uint32_t kOutRowBytes = kFrameLen * CH * 2;  // PCM bytes of one full frame = tensor-map row pitch
+    static constexpr int kSliceBytes = kSliceLen * CH * 2;        // PCM bytes one lane produces per slice
+    static constexpr int kRowBytes = S * kSliceBytes;             // ... per group
+    static constexpr int kGroupSamples = S * kSliceLen;           // per channel
+    static constexpr int kTileBytes = 32 * kRowBytes;             // one warp's tile
     static constexpr int kWarpBytes = NB * kTileBytes;
-    static constexpr int kInRing = 4;                    // 16-byte input vectors in flight per lane
-    static constexpr int kInWarpBytes = kInRing * 32 * 16; // slot-major: slot s of lane l at s*512 + l*16
-    static_assert(S % 2 == 1, "S must be odd (bank-conflict-free staging)");
+    static constexpr int kInRing = 4;                             // 16-byte input vectors in flight per lane
+    static constexpr int kInWarpBytes = kInRing * 32 * 16;        // slot-major: slot s of lane l at s*512 + l*16
+    static_assert((kRowBytes / 16) % 2 == 1 && kRowBytes % 16 == 0, "row pitch must be an odd multiple of 16 bytes");
     static_assert(kTileBytes % 128 == 0, "TMA tiles must be 128-byte aligned");
 };
 
-__device__ __forceinline__ void bulk_store_s2g(void *gptr, uint32_t saddr, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(saddr), "r"(bytes)
-                 : "memory");
-}
 __device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, uint32_t saddr, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
@@ -516,7 +514,7 @@ __device__ __forceinline__ void bulk_wait_read()
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr) // L2 only: the ring is the cache
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
@@ -536,15 +534,21 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
-template <int S, int NB, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
-decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
-                     const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
-                     const __grid_constant__ CUtensorMap out_map, int use_map)
+__device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b)
 {
-    using Cfg = StereoCfg<S, NB>;
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+
+template <int CH, int S, int NB, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
+decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
+                   const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
+                   const __grid_constant__ CUtensorMap out_map, int use_map)
+{
+    using Cfg = FastCfg<CH, S, NB>;
     constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kRowWords = Cfg::kOutRowBytes / 4;
+    constexpr uint32_t kSliceWords = Cfg::kSliceBytes / 4;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
@@ -569,34 +573,38 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
     const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
     if (nsl_max == 0) return;
     const uint32_t nsamp_min = __reduce_min_sync(kFull, nsamp);
-    // regular warp: lane l's frame sits exactly l rows of 20480 bytes below lane 0's
+    // regular warp: lane l's frame sits exactly l rows (one full frame of PCM each) below lane 0's
     const uint64_t out0 = __shfl_sync(kFull, out_byte, 0);
-    const bool regular = use_map && __all_sync(kFull, nsamp != 0 && out_byte == out0 + (uint64_t)lane * kOutRowBytes);
-    int map_c1 = (int)(out0 / kOutRowBytes);                 // tensor-map row of lane 0's frame start
-    int map_c0 = (int)((out0 % kOutRowBytes) / 4);           // 32-bit word inside that row
+    const bool regular = use_map && __all_sync(kFull, nsamp != 0 && out_byte == out0 + (uint64_t)lane * Cfg::kOutRowBytes);
+    int map_c1 = (int)(out0 / Cfg::kOutRowBytes);       // tensor-map row of lane 0's frame start
+    int map_c0 = (int)((out0 % Cfg::kOutRowBytes) / 4); // 32-bit word inside that row
 
     const uint8_t *fp = arena + rec.in_off;
     Chain a, b;
-    const uint8_t *sp = fp + 40;                                    // first slice word (8-byte aligned)
+    const uint8_t *sp = fp + 8 + 16 * CH;                           // first slice word (8-byte aligned)
     const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 8);
     const uint4 *vp = reinterpret_cast<const uint4 *>(sp - skew);    // 16-byte aligned superset
-    const uint32_t nvec = nslices ? (skew + nslices * 16 + 15) / 16 : 0; // vectors holding any byte of this frame's slices
-    // input ring: vector j of this lane lives in slot j % 4; cp.async keeps three vectors in flight
+    const uint32_t nvec = nslices ? (skew + nslices * 8 * CH + 15) / 16 : 0; // vectors holding any byte of the slices
+    // input ring: vector j of this lane lives in slot j % 4
     const uint32_t in_ring = smem_u32(smem + kLutBytes) + (THREADS / 32) * Cfg::kWarpBytes +
                              (threadIdx.x >> 5) * Cfg::kInWarpBytes + lane * 16;
     auto fetch = [&](uint32_t j) {
         if (j < nvec) cp_async16(in_ring + (j & 3) * 512, vp + j);
-        cp_async_commit();
     };
+    // stereo: one vector per slice, three in flight.  mono: one vector per two slices, fetched on even slices.
     fetch(0);
+    cp_async_commit();
     fetch(1);
-    fetch(2);
+    cp_async_commit();
+    if (CH == 2) {
+        fetch(2);
+        cp_async_commit();
+    }
+    a = Chain{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
+    b = a;
     if (nslices) {
         load_lms(a, fp + 8);
-        load_lms(b, fp + 24);
-    } else {
-        a = Chain{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
-        b = a;
+        if (CH == 2) load_lms(b, fp + 24);
     }
     uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
     const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
@@ -614,53 +622,73 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
             bulk_wait_read<NB - 1>();
             __syncwarp();
         }
-        fetch(k + 3);
-        cp_async_wait<2>(); // vectors k and k + 1 have landed (only k + 2 and k + 3 may still be in flight)
+        if (CH == 2) {
+            fetch(k + 3);
+            cp_async_commit();
+            cp_async_wait<2>(); // vectors k and k + 1 have landed (only k + 2 and k + 3 may still be in flight)
+        } else {
+            if ((k & 1) == 0) fetch(k / 2 + 2);
+            cp_async_commit();
+            cp_async_wait<2>(); // everything fetched up to two slices ago has landed: vectors <= (k + 1) / 2
+        }
         if (k < nslices) {
-            // slice k = bytes [skew + 16k, skew + 16k + 16) of the vector stream: no alignment selects needed
-            const uint2 ra = lds64(in_ring + (k & 3) * 512 + skew);
-            const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
-            const uint32_t a_hi = ra.x, a_lo = ra.y, b_hi = rb.x, b_lo = rb.y;
-            const uint2 wa = make_uint2(bswap32(a_hi), bswap32(a_lo));
-            const uint2 wb = make_uint2(bswap32(b_hi), bswap32(b_lo));
-            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
-            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
-            uint32_t o[20];
-            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-            const uint32_t dst_s = row + in_row * 80;
+            const uint32_t dst_s = row + in_row * Cfg::kSliceBytes;
+            if (CH == 2) {
+                // slice k = bytes [skew + 16k, skew + 16k + 16) of the vector stream: no alignment selects needed
+                const uint2 ra = lds64(in_ring + (k & 3) * 512 + skew);
+                const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
+                const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
+                const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
+                const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+                const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+                uint32_t o[20];
+                PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
 #pragma unroll
-            for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+                // slice k = bytes [skew + 8k, skew + 8k + 8) of the vector stream
+                const uint32_t byte = skew + 8 * k;
+                const uint2 ra = lds64(in_ring + ((byte >> 4) & 3) * 512 + (byte & 8));
+                const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
+                const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+                int16_t r[20];
+                SingleLoop<0>::run(a, row_a, wa, r);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) // 40 bytes per slice: rows stay 8-byte aligned
+                    sts64(dst_s + i * 8, __byte_perm((uint32_t)(uint16_t)r[4 * i], (uint32_t)(uint16_t)r[4 * i + 1], 0x5410),
+                          __byte_perm((uint32_t)(uint16_t)r[4 * i + 2], (uint32_t)(uint16_t)r[4 * i + 3], 0x5410));
+            }
         }
         ++in_row;
         if (in_row == S || k + 1 == nsl_max) {
             fence_async_smem(); // staging stores -> visible to the async proxy
             __syncwarp();
-            const bool whole = regular && in_row == S && first + S * kSliceLen <= nsamp_min &&
-                               map_c0 + S * kSliceLen <= (int)(kOutRowBytes / 4);
+            const bool whole = regular && in_row == S && first + Cfg::kGroupSamples <= nsamp_min &&
+                               map_c0 + S * kSliceWords <= kRowWords;
             if (whole) { // every lane staged S full slices: one tensor store for the warp
                 if (lane == 0) tensor_store_2d(&out_map, tile, map_c0, map_c1);
             } else if (first < nsamp) {
                 // Irregular warp or group: every lane copies its own row with 16-byte loads/stores.  Samples past nsamp
                 // (partial last slice, :320-325) are not emitted.
-                const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * 4;
-                uint8_t *dst = op + (uint64_t)first * 4;
+                const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * (2 * CH);
+                uint8_t *dst = op + (uint64_t)first * (2 * CH);
                 uint32_t t = 0;
                 for (; t + 16 <= bytes; t += 16) {
                     uint4 v;
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(row + t));
                     *reinterpret_cast<uint4 *>(dst + t) = v;
                 }
-                for (; t < bytes; t += 4) { // 1..3 trailing (L, R) words when nsamp % 4 != 0
-                    uint32_t v;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(row + t));
-                    *reinterpret_cast<uint32_t *>(dst + t) = v;
+                for (; t < bytes; t += 2) { // trailing samples when the byte count is not a multiple of 16
+                    uint16_t v;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(row + t));
+                    *reinterpret_cast<uint16_t *>(dst + t) = v;
                 }
             }
             bulk_commit();
             first += in_row * kSliceLen;
-            map_c0 += in_row * kSliceLen;
-            if (map_c0 >= (int)(kOutRowBytes / 4)) {
-                map_c0 -= (int)(kOutRowBytes / 4);
+            map_c0 += in_row * kSliceWords;
+            if (map_c0 >= (int)kRowWords) {
+                map_c0 -= (int)kRowWords;
                 map_c1 += 1;
             }
             in_row = 0;
@@ -670,10 +698,10 @@ decode_stereo_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restri
     bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read every tile
 }
 
-// Encodes the tensor map that views the output arena as rows of 20480 bytes (one full stereo frame) of 32-bit words;
+// Encodes the tensor map that views the output arena as rows of `row_bytes` (the PCM of one full frame) of 32-bit words;
 // box = box_words x 32 rows.  Returns false when the driver entry point is unavailable or the arena does not qualify
 // (the kernel then uses per-lane bulk copies only).
-static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words)
+static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words, uint32_t row_bytes)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -691,10 +719,10 @@ static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint
             cudaGetLastError();
     }
     if (!encode || (reinterpret_cast<uintptr_t>(d_out) & 15) || out_bytes == 0) return false;
-    const uint64_t rows = (out_bytes + kOutRowBytes - 1) / kOutRowBytes;
+    const uint64_t rows = (out_bytes + row_bytes - 1) / row_bytes;
     if (rows > 0x7fffffffull) return false;
-    const cuuint64_t dims[2] = {kOutRowBytes / 4, rows};
-    const cuuint64_t strides[1] = {kOutRowBytes};
+    const cuuint64_t dims[2] = {row_bytes / 4, rows};
+    const cuuint64_t strides[1] = {row_bytes};
     const cuuint32_t box[2] = {box_words, 32};
     const cuuint32_t estr[2] = {1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -745,36 +773,36 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     }
 }
 
-template <int S, int NB, int THREADS>
-static cudaError_t launch_stereo(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
-                                 const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
+template <int CH, int S, int NB, int THREADS>
+static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
+                               const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
 {
-    const size_t smem = kLutAlign + kLutBytes +
-                        (size_t)(THREADS / 32) * (StereoCfg<S, NB>::kWarpBytes + StereoCfg<S, NB>::kInWarpBytes);
+    using Cfg = FastCfg<CH, S, NB>;
+    const size_t smem = kLutAlign + kLutBytes + (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_stereo_kernel<S, NB, THREADS>,
+        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     CUtensorMap map;
     memset(&map, 0, sizeof map);
-    const int use_map = make_out_map(&map, d_out, out_bytes, S * kSliceLen) ? 1 : 0;
+    const int use_map = make_out_map(&map, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes) ? 1 : 0;
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    decode_stereo_kernel<S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
-                                                                                 d_out, map, use_map);
+    decode_fast_kernel<CH, S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
+                                                                                   d_out, map, use_map);
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
-                          bool all_stereo, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
+                          uint32_t uniform_ch, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
                           cudaStream_t s, int *n_launches)
 {
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
     cudaError_t e;
-    if (all_stereo) {
+    if (uniform_ch == 2) {
         // QOA_B200_DEC_VARIANT selects a tuning variant (development aid; the default is the measured best).
         static int variant = -1;
         if (variant < 0) {
@@ -782,15 +810,14 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
             variant = v ? atoi(v) : 0;
         }
         switch (variant) {
-        case 1: e = launch_stereo<3, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 2: e = launch_stereo<3, 1, 192>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 3: e = launch_stereo<3, 1, 640>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 4: e = launch_stereo<3, 1, 352>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 5: e = launch_stereo<3, 1, 128>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 6: e = launch_stereo<5, 1, 224>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 7: e = launch_stereo<3, 1, 704>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        default: e = launch_stereo<3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 1: e = launch_fast<2, 3, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 2: e = launch_fast<2, 3, 1, 192>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 3: e = launch_fast<2, 3, 1, 640>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 5: e = launch_fast<2, 3, 1, 128>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        default: e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         }
+    } else if (uniform_ch == 1) {
+        e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else {
         const uint64_t n_units = n_frames * max_ch;
         const uint64_t blocks = (n_units + kGenThreads - 1) / kGenThreads;

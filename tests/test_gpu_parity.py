@@ -153,6 +153,21 @@ def test_stereo_batch_fast_path(eng):
     check_decode_batch(eng, enc, 0)
 
 
+def test_mono_batch_fast_path(eng):
+    """All-mono batches take the same TMA-staged kernel with one chain per thread (6 slices per staged row)."""
+    lens = [5120, 5120 * 3, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 1, 4080, 2 * 5120 + 3081, 5120 * 40 + 119]
+    pcm_list = [signals.synth_pcm(4, i, 1, n, "noise" if i % 3 == 0 else "music") for i, n in enumerate(lens)]
+    descs = [(1, 22050, n) for n in lens]
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * len(lens)
+    enc = [o.tobytes() for o in outs]
+    for p, d, e in zip(pcm_list, descs, enc):
+        assert e == ob.encode_all(p, *d)[1]
+    check_decode_batch(eng, enc, 0)
+    check_decode_batch(eng, enc * 7, 1)      # enough frames for regular 32-frame warps and stream-straddling warps
+    check_decode_batch(eng, [e[:len(e) - 9] for e in enc[:4]] + enc, 0)  # truncated mono streams in the batch
+
+
 def test_noise_brute_equivalence(eng):
     """White noise is the worst case for the reference's pruning; the GPU's full search must pick the same winners."""
     pcm = signals.synth_pcm(2, 5, 2, 30000, "noise")
