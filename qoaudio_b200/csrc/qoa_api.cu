@@ -844,9 +844,13 @@ static int plan_run_host(qoa_b200_decode_plan *plan, int16_t *const *out, const 
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint64_t> off(n, 0);
     uint64_t total = 0;
+    // Every stream gets a slot that starts on a multiple of one full frame of PCM (5120 x channels values) when the
+    // batch takes the mono / stereo fast path: frames of consecutive streams then stay on the 2-D tensor map's row
+    // lattice, so boxes that span a stream boundary still leave through one tensor store (measured: +4 %).
+    const uint64_t slot = plan->uniform_ch ? (uint64_t)QOA_B200_FRAME_LEN * plan->uniform_ch : 8;
     for (size_t i = 0; i < n; ++i) {
         off[i] = total;
-        if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + 7) & ~(uint64_t)7;
+        if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + slot - 1) / slot * slot;
     }
     int16_t *d_out = static_cast<int16_t *>(ctx->alloc((total + 8) * sizeof(int16_t)));
     if (!d_out) {

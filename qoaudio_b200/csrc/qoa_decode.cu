@@ -476,10 +476,11 @@ struct SingleLoop<20> {
 //   * regular warps (32 consecutive full frames of one stream, i.e. rows exactly one frame of PCM apart in the
 //     output): ONE 2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = 60 words x 32 rows of a tensor
 //     map that views the output arena as rows of one frame of PCM) — no copy-out instructions at all;
-//   * everything else (warps that straddle two streams, short last frames, partial slices, the group that crosses a
-//     row of the arena-wide map; ~8 % of the groups): every lane copies its own row with 16-byte shared loads /
-//     global stores.  (Per-lane cp.async.bulk copies were measured first: UBLKCP takes uniform operands, so the
-//     compiler serialises it over the 32 lanes — ~480 instructions per group.)
+//   * everything else (warps that straddle two streams, short last frames, partial slices; ~8 % of the groups):
+//     the warp copies the tile row by row with 16-byte shared loads / global stores, one half-warp per 240-byte row.
+//     (Measured alternatives: per-lane cp.async.bulk copies — UBLKCP takes uniform operands, so the compiler
+//     serialises it over the 32 lanes, ~480 instructions per group; per-lane 16-byte stores — 32 scattered sectors
+//     per instruction, groups on that path ran 1.8x slower.)
 // The row pitch (240 bytes) is an odd multiple of 16: the 128-bit staging stores of a quarter-warp hit eight distinct
 // bank groups.  NB tiles per warp form a ring.
 // Slice words arrive through a per-lane ring of four 16-byte vectors filled by cp.async two to three slices ahead
@@ -495,10 +496,12 @@ struct FastCfg {
     static constexpr int kGroupSamples = S * kSliceLen;           // per channel
     static constexpr int kTileBytes = 32 * kRowBytes;             // one warp's tile
     static constexpr int kWarpBytes = NB * kTileBytes;
+    static constexpr int kBoxRows = 8;                            // rows (frames) per tensor store
     static constexpr int kInRing = 4;                             // 16-byte input vectors in flight per lane
     static constexpr int kInWarpBytes = kInRing * 32 * 16;        // slot-major: slot s of lane l at s*512 + l*16
     static_assert((kRowBytes / 16) % 2 == 1 && kRowBytes % 16 == 0, "row pitch must be an odd multiple of 16 bytes");
-    static_assert(kTileBytes % 128 == 0, "TMA tiles must be 128-byte aligned");
+    static_assert((kBoxRows * kRowBytes) % 128 == 0 && (kBoxRows * (kSlicesPerFrame % S) * kSliceBytes) % 128 == 0,
+                  "every box handed to the TMA engine must start 128-byte aligned in shared memory");
 };
 
 __device__ __forceinline__ void tensor_store_2d(const CUtensorMap *map, uint32_t saddr, int c0, int c1)
@@ -543,9 +546,11 @@ template <int CH, int S, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
 decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
-                   const __grid_constant__ CUtensorMap out_map, int use_map)
+                   const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap out_map_rem,
+                   int use_map)
 {
     using Cfg = FastCfg<CH, S, NB>;
+    constexpr uint32_t kRem = kSlicesPerFrame % S; // slices in the last group of a full frame (its own tensor map)
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kRowWords = Cfg::kOutRowBytes / 4;
     constexpr uint32_t kSliceWords = Cfg::kSliceBytes / 4;
@@ -572,11 +577,20 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
     const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
     const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
     if (nsl_max == 0) return;
-    const uint32_t nsamp_min = __reduce_min_sync(kFull, nsamp);
-    // regular warp: lane l's frame sits exactly l rows (one full frame of PCM each) below lane 0's
-    const uint64_t out0 = __shfl_sync(kFull, out_byte, 0);
-    const bool regular = use_map && __all_sync(kFull, nsamp != 0 && out_byte == out0 + (uint64_t)lane * Cfg::kOutRowBytes);
-    int map_c1 = (int)(out0 / Cfg::kOutRowBytes);       // tensor-map row of lane 0's frame start
+    // The 32 rows of a warp's tile go out as 32 / RB tensor stores of RB rows each.  A box is "regular" when its RB
+    // frames sit exactly one full frame of PCM apart in the output (same stream, consecutive frames): only boxes that
+    // contain a stream boundary (or idle lanes) take the row-by-row copy path.
+    constexpr uint32_t RB = Cfg::kBoxRows;
+    const uint32_t leader = lane & ~(RB - 1);
+    const uint64_t out0 = __shfl_sync(kFull, out_byte, leader);
+    const bool lane_ok = use_map && nsamp != 0 && out_byte == out0 + (uint64_t)(lane - leader) * Cfg::kOutRowBytes;
+    const uint32_t ok_mask = __ballot_sync(kFull, lane_ok);
+    const uint32_t box_mask = (RB == 32 ? 0xffffffffu : ((1u << RB) - 1u)) << leader;
+    const bool regular = (ok_mask & box_mask) == box_mask;
+    uint32_t nsamp_min = nsamp; // over the box
+#pragma unroll
+    for (uint32_t m = RB / 2; m >= 1; m >>= 1) nsamp_min = min(nsamp_min, __shfl_xor_sync(kFull, nsamp_min, m));
+    int map_c1 = (int)(out0 / Cfg::kOutRowBytes);       // tensor-map row of the box leader's frame start
     int map_c0 = (int)((out0 % Cfg::kOutRowBytes) / 4); // 32-bit word inside that row
 
     const uint8_t *fp = arena + rec.in_off;
@@ -609,19 +623,31 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
     uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
     const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
     const uint32_t warp_tiles = smem_u32(smem + kLutBytes) + (threadIdx.x >> 5) * Cfg::kWarpBytes;
+    // per-warp table {PCM pointer, nsamp} of the 32 rows for the row-by-row copy path
+    const uint32_t rows_meta = smem_u32(smem + kLutBytes) + (THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes) +
+                               (threadIdx.x >> 5) * 512;
+    {
+        const uint64_t p64 = reinterpret_cast<uint64_t>(op);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rows_meta + lane * 16), "r"((uint32_t)p64),
+                     "r"((uint32_t)(p64 >> 32)), "r"(nsamp), "r"(0u)
+                     : "memory");
+        __syncwarp();
+    }
 
     uint32_t ring = 0;   // tile of the ring being filled
     uint32_t in_row = 0; // slices already staged in it
     uint32_t first = 0;  // per-channel sample index of the tile's first sample
+    uint32_t pitch = Cfg::kRowBytes; // row pitch of the tile being filled: the warp's last, shorter group is staged densely
 
 #pragma unroll 1
     for (uint32_t k = 0; k < nsl_max; ++k) {
         const uint32_t tile = warp_tiles + ring * Cfg::kTileBytes;
-        const uint32_t row = tile + lane * Cfg::kRowBytes;
         if (in_row == 0) { // the copies that last read this tile have drained it
             bulk_wait_read<NB - 1>();
             __syncwarp();
+            pitch = min((uint32_t)S, nsl_max - k) * Cfg::kSliceBytes; // TMA reads the tile densely: pitch = box width
         }
+        const uint32_t row = tile + lane * pitch;
         if (CH == 2) {
             fetch(k + 3);
             cp_async_commit();
@@ -663,25 +689,38 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
         if (in_row == S || k + 1 == nsl_max) {
             fence_async_smem(); // staging stores -> visible to the async proxy
             __syncwarp();
-            const bool whole = regular && in_row == S && first + Cfg::kGroupSamples <= nsamp_min &&
-                               map_c0 + S * kSliceWords <= kRowWords;
-            if (whole) { // every lane staged S full slices: one tensor store for the warp
-                if (lane == 0) tensor_store_2d(&out_map, tile, map_c0, map_c1);
-            } else if (first < nsamp) {
-                // Irregular warp or group: every lane copies its own row with 16-byte loads/stores.  Samples past nsamp
-                // (partial last slice, :320-325) are not emitted.
-                const uint32_t bytes = min(in_row * (uint32_t)kSliceLen, nsamp - first) * (2 * CH);
-                uint8_t *dst = op + (uint64_t)first * (2 * CH);
-                uint32_t t = 0;
-                for (; t + 16 <= bytes; t += 16) {
-                    uint4 v;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(row + t));
-                    *reinterpret_cast<uint4 *>(dst + t) = v;
-                }
-                for (; t < bytes; t += 2) { // trailing samples when the byte count is not a multiple of 16
-                    uint16_t v;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(row + t));
-                    *reinterpret_cast<uint16_t *>(dst + t) = v;
+            const bool whole = regular && (in_row == S || in_row == kRem) && first + in_row * kSliceLen <= nsamp_min &&
+                               (use_map == 2 || map_c0 + in_row * kSliceWords <= kRowWords);
+            const uint32_t whole_rows = __ballot_sync(kFull, whole); // bit r: row r leaves through a tensor store
+            if (whole && lane == leader) // every lane of the box staged the same number of full slices
+                tensor_store_2d(in_row == S ? &out_map : &out_map_rem, tile + leader * pitch, map_c0, map_c1);
+            if (whole_rows != kFull) {
+                // Rows of irregular boxes: the warp copies them one half-warp per row (16 lanes x 16 bytes cover a
+                // 240-byte row), so every store instruction writes two contiguous runs instead of 32 scattered 16-byte
+                // pieces.  Samples past a row's nsamp (partial last slice, :320-325) are not emitted.
+#pragma unroll 1
+                for (uint32_t it = 0; it < 16; ++it) {
+                    if (((whole_rows >> (2 * it)) & 3u) == 3u) continue;
+                    const uint32_t r = it * 2 + (lane >> 4);
+                    if ((whole_rows >> r) & 1u) continue;
+                    const uint32_t off = (lane & 15) * 16;
+                    const uint2 pr = lds64(rows_meta + r * 16);
+                    uint32_t ns;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ns) : "r"(rows_meta + r * 16 + 8));
+                    const uint32_t bytes = first < ns ? min(in_row * (uint32_t)kSliceLen, ns - first) * (2 * CH) : 0u;
+                    uint8_t *dst = reinterpret_cast<uint8_t *>(((uint64_t)pr.y << 32) | pr.x) + (uint64_t)first * (2 * CH);
+                    const uint32_t src = tile + r * pitch;
+                    if (off + 16 <= bytes) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
+                        *reinterpret_cast<uint4 *>(dst + off) = v;
+                    } else {
+                        for (uint32_t t = off; t < bytes; t += 2) { // trailing samples of a row that is not a multiple of 16 bytes
+                            uint16_t v;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(src + t));
+                            *reinterpret_cast<uint16_t *>(dst + t) = v;
+                        }
+                    }
                 }
             }
             bulk_commit();
@@ -699,9 +738,13 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
 }
 
 // Encodes the tensor map that views the output arena as rows of `row_bytes` (the PCM of one full frame) of 32-bit words;
-// box = box_words x 32 rows.  Returns false when the driver entry point is unavailable or the arena does not qualify
+// box = box_words x box_rows.  Returns 0 when the driver entry point is unavailable or the arena does not qualify
 // (the kernel then uses per-lane bulk copies only).
-static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words, uint32_t row_bytes)
+// Returns 0 when no map could be made, 2 when the map's rows overlap (dim 0 is extended by one box beyond the row pitch,
+// so a box may start anywhere in a row and run into the next one), 1 when the driver refused overlapping rows (boxes
+// that would cross a row end are then left to the per-lane copy path).
+static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words, uint32_t row_bytes,
+                        uint32_t box_rows)
 {
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -718,16 +761,20 @@ static bool make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint
         else
             cudaGetLastError();
     }
-    if (!encode || (reinterpret_cast<uintptr_t>(d_out) & 15) || out_bytes == 0) return false;
-    const uint64_t rows = (out_bytes + row_bytes - 1) / row_bytes;
-    if (rows > 0x7fffffffull) return false;
-    const cuuint64_t dims[2] = {row_bytes / 4, rows};
+    if (!encode || (reinterpret_cast<uintptr_t>(d_out) & 15) || out_bytes == 0) return 0;
+    const uint64_t rows = (out_bytes + row_bytes - 1) / row_bytes + 1;
+    if (rows > 0x7fffffffull) return 0;
     const cuuint64_t strides[1] = {row_bytes};
-    const cuuint32_t box[2] = {box_words, 32};
+    const cuuint32_t box[2] = {box_words, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    for (int overlap = 1; overlap >= 0; --overlap) {
+        const cuuint64_t dims[2] = {row_bytes / 4 + (overlap ? box_words : 0), rows};
+        if (encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d_out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            return overlap ? 2 : 1;
+    }
+    return 0;
 }
 
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
@@ -778,7 +825,7 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
                                const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
 {
     using Cfg = FastCfg<CH, S, NB>;
-    const size_t smem = kLutAlign + kLutBytes + (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes);
+    const size_t smem = kLutAlign + kLutBytes + (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes + 512);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS>,
@@ -786,13 +833,19 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    CUtensorMap map;
+    CUtensorMap map, map_rem;
     memset(&map, 0, sizeof map);
-    const int use_map = make_out_map(&map, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes) ? 1 : 0;
+    memset(&map_rem, 0, sizeof map_rem);
+    constexpr uint32_t kRem = kSlicesPerFrame % S;
+    int use_map = make_out_map(&map, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes, Cfg::kBoxRows);
+    if (use_map && kRem) // the last group of a full frame holds 256 % S slices: same tile pitch, narrower box
+        use_map = std::min(use_map, make_out_map(&map_rem, d_out, out_bytes, kRem * Cfg::kSliceBytes / 4, Cfg::kOutRowBytes,
+                                                 Cfg::kBoxRows));
+    if (const char *dbg = getenv("QOA_B200_TMAP")) use_map = std::min(use_map, atoi(dbg)); // development aid: 0 = no tensor stores, 1 = no overlapping rows
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
     decode_fast_kernel<CH, S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
-                                                                                   d_out, map, use_map);
+                                                                                   d_out, map, map_rem, use_map);
     return cudaGetLastError();
 }
 
