@@ -632,7 +632,7 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     }
     plan->n_frames = plan->frame_base[n];
     plan->max_ch = max_ch;
-    plan->uniform_ch = (uniform && plan->n_frames > 0 && (first_ch == 1 || first_ch == 2)) ? first_ch : 0;
+    plan->uniform_ch = (uniform && plan->n_frames > 0 && first_ch >= 1 && first_ch <= 8) ? first_ch : 0;
     if (plan->n_frames) {
         if (!plan->d_recs) plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
         if (!plan->d_recs) {
@@ -847,7 +847,7 @@ static int plan_run_host(qoa_b200_decode_plan *plan, int16_t *const *out, const 
     // Every stream gets a slot that starts on a multiple of one full frame of PCM (5120 x channels values) when the
     // batch takes the mono / stereo fast path: frames of consecutive streams then stay on the 2-D tensor map's row
     // lattice, so boxes that span a stream boundary still leave through one tensor store (measured: +4 %).
-    const uint64_t slot = plan->uniform_ch ? (uint64_t)QOA_B200_FRAME_LEN * plan->uniform_ch : 8;
+    const uint64_t slot = (plan->uniform_ch == 1 || plan->uniform_ch == 2) ? (uint64_t)QOA_B200_FRAME_LEN * plan->uniform_ch : 8;
     for (size_t i = 0; i < n; ++i) {
         off[i] = total;
         if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + slot - 1) / slot * slot;

@@ -777,6 +777,155 @@ static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint3
     return 0;
 }
 
+// ---- uniform multi-channel batches (3..8 channels) ---------------------------------------------------------------
+// One thread = one (frame, channel pair): the same two-chain slice loop as stereo (an odd channel count leaves the
+// last pair with one live chain).  The P = ceil(ch / 2) lanes of a frame are neighbours in the warp, 32 / P frames
+// per warp.  Every lane writes its pair's samples into its FRAME's row of a per-warp shared-memory tile
+// ([frames][S slices x 20 samples x ch] interleaved i16, S = 1 for even and 2 for odd channel counts so that a row is a
+// multiple of 16 bytes); after S slices the warp copies the tile out row by row, one half-warp per 256-byte run, so
+// global stores are contiguous runs of the interleaved PCM.  Slice words arrive through a per-lane cp.async ring
+// three slices ahead.  Requirements (host-checked): every frame has `ch` channels and starts 16-byte aligned.
+constexpr int kMultiThreads = 256;
+constexpr int kMultiTileBytes = 4608; // largest tile: 7 channels = 8 frames x (2 slices x 280 B + 16 B pad)
+
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+
+__global__ void __launch_bounds__(kMultiThreads, 2)
+decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames, uint32_t ch,
+                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
+{
+    constexpr uint32_t kFull = 0xffffffffu;
+    constexpr int kWarps = kMultiThreads / 32;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
+    uint8_t *smem = smem_raw + pad;
+    fill_lut(smem);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t P = (ch + 1) / 2;           // channel pairs per frame
+    const uint32_t fpw = 32 / P;               // frames per warp
+    const uint32_t S = (ch & 1) ? 2u : 1u;     // slices per tile row
+    const uint32_t row_bytes = S * kSliceLen * ch * 2;
+    const uint32_t pitch = row_bytes + 16;     // pad: neighbouring rows start in different bank groups
+    const uint32_t fl = lane / P, p = lane - fl * P; // frame within the warp, pair within the frame
+    const uint64_t fi = ((uint64_t)blockIdx.x * kWarps + warp) * fpw + fl;
+
+    uint32_t nsamp = 0;
+    uint8_t *op = reinterpret_cast<uint8_t *>(out);
+    FrameRec rec;
+    rec.in_off = 0;
+    if (fl < fpw && fi < n_frames) {
+        rec = recs[fi];
+        const uint64_t ob = out_base[rec.stream];
+        if (ob != ~0ull) {
+            nsamp = rec.nsamp;
+            op += (ob + rec.out_rel) * 2;
+        }
+    }
+    const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
+    const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
+    if (nsl_max == 0) return;
+
+    const uint32_t c0 = 2 * p;
+    const bool two = c0 + 1 < ch; // the last pair of an odd channel count has one live chain (the other mirrors it)
+    const uint8_t *fp = arena + rec.in_off;
+    Chain a, b;
+    a = Chain{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
+    b = a;
+    if (nslices) {
+        load_lms(a, fp + 8 + 16 * c0);
+        load_lms(b, fp + 8 + 16 * (two ? c0 + 1 : c0));
+    }
+    const uint8_t *sp = fp + 8 + 16 * ch + 8 * c0; // this pair's word(s) of slice 0; slice k is k * ch * 8 bytes further
+    const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
+    // shared memory after the LUT: per warp [tile: frames x pitch <= kMultiTileBytes][ring: 4 x 32 x 16][row table: 32 x 16]
+    const uint32_t warp_base = smem_u32(smem + kLutBytes) + warp * (kMultiTileBytes + 2048 + 512);
+    const uint32_t tile = warp_base;
+    const uint32_t in_ring = warp_base + kMultiTileBytes + lane * 16;
+    const uint32_t rows_meta = warp_base + kMultiTileBytes + 2048;
+    if (p == 0) { // one table entry per frame: {PCM pointer, nsamp}
+        const uint64_t p64 = reinterpret_cast<uint64_t>(op);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rows_meta + fl * 16), "r"((uint32_t)p64),
+                     "r"((uint32_t)(p64 >> 32)), "r"(fl < fpw ? nsamp : 0u), "r"(0u)
+                     : "memory");
+    }
+    auto fetch = [&](uint32_t k) { // slice k's word(s) into ring slot k % 4
+        if (k < nslices) {
+            const uint8_t *g = sp + (uint64_t)k * ch * 8;
+            cp_async8(in_ring + (k & 3) * 512, g);
+            if (two) cp_async8(in_ring + (k & 3) * 512 + 8, g + 8);
+        }
+        cp_async_commit();
+    };
+    fetch(0);
+    fetch(1);
+    fetch(2);
+    __syncwarp();
+
+    const uint32_t row = tile + fl * pitch + c0 * 2; // this pair's first sample inside its frame's row
+    uint32_t in_row = 0, first = 0;
+#pragma unroll 1
+    for (uint32_t k = 0; k < nsl_max; ++k) {
+        fetch(k + 3);
+        cp_async_wait<3>(); // slice k's words have landed
+        if (k < nslices) {
+            const uint2 ra = lds64(in_ring + (k & 3) * 512);
+            const uint2 rb = two ? lds64(in_ring + (k & 3) * 512 + 8) : ra;
+            const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
+            const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+            uint32_t o[20];
+            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+            const uint32_t dst = row + in_row * (kSliceLen * ch * 2);
+            if (!(ch & 1)) { // even channel counts: the pair is one aligned 32-bit word per sample
+#pragma unroll
+                for (int i = 0; i < 20; ++i) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + i * ch * 2), "r"(o[i]) : "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) {
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * ch * 2), "h"((uint16_t)(o[i] & 0xffffu)) : "memory");
+                    if (two) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * ch * 2 + 2), "h"((uint16_t)(o[i] >> 16)) : "memory");
+                }
+            }
+        }
+        ++in_row;
+        if (in_row == S || k + 1 == nsl_max) {
+            __syncwarp();
+            // copy the tile out: one half-warp per 256-byte run of a row
+            const uint32_t runs = (row_bytes + 255) / 256;
+            for (uint32_t it = lane >> 4; it < fpw * runs; it += 2) {
+                const uint32_t r = it / runs, run = it - r * runs;
+                const uint32_t off = run * 256 + (lane & 15) * 16;
+                const uint2 pr = lds64(rows_meta + r * 16);
+                uint32_t ns;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ns) : "r"(rows_meta + r * 16 + 8));
+                // Samples past nsamp (partial last slice, :320-325) are not emitted.
+                const uint32_t bytes = first < ns ? min(in_row * (uint32_t)kSliceLen, ns - first) * ch * 2 : 0u;
+                uint8_t *gdst = reinterpret_cast<uint8_t *>(((uint64_t)pr.y << 32) | pr.x) + (uint64_t)first * ch * 2;
+                const uint32_t src = tile + r * pitch;
+                if (off + 16 <= bytes) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + off));
+                    *reinterpret_cast<uint4 *>(gdst + off) = v;
+                } else {
+                    for (uint32_t t = off; t < min(bytes, off + 16); t += 2) {
+                        uint16_t v;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(src + t));
+                        *reinterpret_cast<uint16_t *>(gdst + t) = v;
+                    }
+                }
+            }
+            __syncwarp();
+            first += in_row * kSliceLen;
+            in_row = 0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
 constexpr int kGenThreads = 128;
 
@@ -871,6 +1020,25 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
         }
     } else if (uniform_ch == 1) {
         e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+    } else if (uniform_ch >= 3 && uniform_ch <= 8) {
+        const size_t smem = kLutAlign + kLutBytes + (size_t)(kMultiThreads / 32) * (kMultiTileBytes + 2048 + 512);
+        {
+            const uint32_t pairs = (uniform_ch + 1) / 2, rows = 32 / pairs, sl = (uniform_ch & 1) ? 2 : 1;
+            if (rows * (sl * kSliceLen * uniform_ch * 2 + 16) > (uint32_t)kMultiTileBytes) return cudaErrorInvalidValue;
+        }
+        static bool configured = false;
+        if (!configured) {
+            e = cudaFuncSetAttribute(decode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const uint32_t fpw = 32 / ((uniform_ch + 1) / 2);
+        const uint64_t warps = (n_frames + fpw - 1) / fpw;
+        const uint64_t blocks = (warps + kMultiThreads / 32 - 1) / (kMultiThreads / 32);
+        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+        decode_multi_kernel<<<(unsigned)blocks, kMultiThreads, smem, s>>>(d_arena, d_recs, n_frames, uniform_ch, d_out_base,
+                                                                          d_out);
+        e = cudaGetLastError();
     } else {
         const uint64_t n_units = n_frames * max_ch;
         const uint64_t blocks = (n_units + kGenThreads - 1) / kGenThreads;

@@ -31,8 +31,8 @@ cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_
 // Frame-parallel decode.  max_ch = largest channel count of any frame in the table; d_out_base[stream] = i16 element
 // offset of the stream's output in d_out (UINT64_MAX = do not write this stream); out_bytes = extent of the output arena
 // that the batch may touch (upper bound of any written byte offset).
-// uniform_ch = 1 or 2 when every frame has that many channels and starts 16-byte aligned in the output (fast path),
-// else 0 (generic path).
+// uniform_ch = 1..8 when every frame has that many channels and starts 16-byte aligned in the output (fast paths:
+// TMA-staged kernel for mono / stereo, pair-per-lane kernel for 3..8 channels), else 0 (generic path).
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,
                           uint32_t uniform_ch, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
                           cudaStream_t s, int *n_launches);

@@ -168,6 +168,21 @@ def test_mono_batch_fast_path(eng):
     check_decode_batch(eng, [e[:len(e) - 9] for e in enc[:4]] + enc, 0)  # truncated mono streams in the batch
 
 
+@pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8])
+def test_multichannel_batch_fast_path(eng, ch):
+    """Uniform 3..8-channel batches take the pair-per-lane kernel (row tiles + contiguous copy-out)."""
+    lens = [5120, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 1, 4080, 5120 * 3 + 3081, 5120 * 9 + 119]
+    pcm_list = [signals.synth_pcm(8, i, ch, n, "noise" if i % 4 == 1 else "music") for i, n in enumerate(lens)]
+    descs = [(ch, 48000, n) for n in lens]
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * len(lens)
+    enc = [o.tobytes() for o in outs]
+    for pcm, d, e in zip(pcm_list, descs, enc):
+        assert e == ob.encode_all(pcm, *d)[1]
+    check_decode_batch(eng, enc, 0)
+    check_decode_batch(eng, enc * 3 + [e[:len(e) - 17] for e in enc[:3]], 1)  # more frames + truncated streams
+
+
 def test_noise_brute_equivalence(eng):
     """White noise is the worst case for the reference's pruning; the GPU's full search must pick the same winners."""
     pcm = signals.synth_pcm(2, 5, 2, 30000, "noise")
