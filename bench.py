@@ -356,6 +356,41 @@ def main():
                                "frac_of_measured_mix_peak": per_gpu_ops / measured["mix"], "traffic": None},
                   "clocks": clocks2}
         batch.close()
+        # e2e: the same shape through qoa_b200_encode_all_batch with pinned HOST buffers (time-chunked pipeline:
+        # H2D of chunk t+1 || kernel of chunk t || D2H of chunk t-1); 8 frames per stream per call
+        if not args.no_e2e:
+            import ctypes as C
+            N = q._native
+            EF = 8
+            per = EF * 5120 * ENC_CH
+            osz = enc_size(ENC_CH, EF * 5120)
+            h_pcm = epcm[:ES * per].cpu().pin_memory()
+            h_enc = torch.empty(ES * osz, dtype=torch.uint8).pin_memory()
+            descs_c = (N.Desc * ES)(*[N.Desc(ENC_CH, ENC_RATE, EF * 5120)] * ES)
+            pp = (C.c_void_p * ES)(*[h_pcm.data_ptr() + 2 * i * per for i in range(ES)])
+            pl = (C.c_size_t * ES)(*([per] * ES))
+            op_ = (C.c_void_p * ES)(*[h_enc.data_ptr() + i * osz for i in range(ES)])
+            oc = (C.c_size_t * ES)(*([osz] * ES))
+            ol = (C.c_size_t * ES)()
+            stt = (C.c_int32 * ES)()
+
+            def enc_e2e_step():
+                rc = N.lib().qoa_b200_encode_all_batch(eng.handle, descs_c, pp, pl, op_, oc, ol, stt, ES)
+                assert rc == 0 and all(v == 0 for v in stt)
+
+            for _ in range(2):
+                enc_e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                enc_e2e_step()
+            torch.cuda.synchronize()
+            dt = reduce_max(time.perf_counter() - t0)
+            encode["e2e"] = {"value": ES * per * world * reps / dt / 1e6, "unit": "Msamples/s",
+                             "h2d_bytes_per_step": ES * per * 2, "d2h_bytes_per_step": ES * osz, "ms_per_step": dt / reps * 1e3,
+                             "api": "qoa_b200_encode_all_batch (pinned host buffers, 8 frames per stream per call)"}
+            del h_pcm, h_enc
         del epcm, eout
 
     # ---------------------------------------------------------------- configs[1]: ONE 54 s stereo stream --------

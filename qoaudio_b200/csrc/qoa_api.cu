@@ -318,6 +318,10 @@ extern "C" int qoa_b200_encode_all_batch_dev(qoa_b200_ctx *ctx, const qoa_b200_d
     return run_encode_jobs(ctx, sc, jobs, d_pcm, d_out, d_lms, s);
 }
 
+static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
+                                      const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
+                                      size_t *out_len, int32_t *status, size_t n, uint64_t total_pcm_values);
+
 extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
                                          const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
                                          size_t *out_len, int32_t *status, size_t n)
@@ -329,6 +333,12 @@ extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc 
         return QOA_B200_E_ARG;
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        uint64_t total = 0;
+        for (size_t i = 0; i < n; ++i) total += pcm_len[i];
+        if (total >= (96ull << 20)) // >= 192 MB of PCM: overlap the copies with the kernel, chunked in time
+            return encode_all_batch_pipelined(ctx, descs, pcm, pcm_len, out, out_cap, out_len, status, n, total);
+    }
     cudaStream_t s = nullptr;
     // lay the valid streams out in two device arenas
     std::vector<uint64_t> pcm_off(n, 0), out_off(n, 0);
@@ -564,6 +574,121 @@ extern "C" int qoa_b200_encoder_batch_get_lms(qoa_b200_encoder_batch *enc, size_
     memcpy(history, st, 16);
     memcpy(weights, st + 4, 16);
     return 0;
+}
+
+// Large host batches: time-chunked software pipeline.  Chunk t holds the next F frames of EVERY stream (the encoder's
+// parallelism is streams x channels, so chunks must keep all streams), the LMS state persists on the device between
+// chunks exactly like encode_frame (src/lib.rs:482), and three internal streams overlap the H2D copy of chunk t + 1,
+// the kernel of chunk t and the D2H copy of chunk t - 1.  Kernels are chained with events (they share the LMS state).
+static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
+                                      const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
+                                      size_t *out_len, int32_t *status, size_t n, uint64_t total_pcm_values)
+{
+    if (ctx->used) CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->last_stream));
+    for (auto &ps : ctx->pipe_streams)
+        if (!ps) CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    // validation exactly as the one-shot path
+    std::vector<qoa_b200_desc> d(descs, descs + n);
+    uint64_t values_per_frame_step = 0; // PCM values one frame of every valid stream holds
+    uint32_t max_frames = 0;
+    for (size_t i = 0; i < n; ++i) {
+        out_len[i] = 0;
+        int st = validate_desc(descs[i]);
+        if (st == QOA_B200_OK && pcm_len[i] != (size_t)descs[i].samples * descs[i].channels) st = QOA_B200_ENC_INVALID_SAMPLES;
+        const size_t need = st == QOA_B200_OK ? qoa_b200_encoded_size(descs[i].channels, descs[i].samples) : 0;
+        if (st == QOA_B200_OK && (out_cap[i] < need || !out[i] || !pcm[i])) st = QOA_B200_ENC_IO_ERROR;
+        status[i] = st;
+        if (st != QOA_B200_OK) {
+            d[i].channels = 0; // skipped by the encoder batch
+            continue;
+        }
+        out_len[i] = need;
+        values_per_frame_step += (uint64_t)QOA_B200_FRAME_LEN * descs[i].channels;
+        max_frames = std::max<uint32_t>(max_frames, (descs[i].samples + QOA_B200_FRAME_LEN - 1) / QOA_B200_FRAME_LEN);
+    }
+    if (values_per_frame_step == 0) return 0;
+    (void)total_pcm_values;
+    const uint32_t frames_per_chunk = (uint32_t)std::max<uint64_t>(1, (48ull << 20) / values_per_frame_step); // ~96 MB of PCM
+    qoa_b200_encoder_batch *enc = nullptr;
+    std::vector<int32_t> new_status(n);
+    int rc = qoa_b200_encoder_batch_new(ctx, d.data(), n, new_status.data(), &enc);
+    if (rc != 0) return rc;
+    {
+        std::vector<uint8_t *> hdr(n, nullptr);
+        for (size_t i = 0; i < n; ++i)
+            if (status[i] == QOA_B200_OK) hdr[i] = out[i];
+        qoa_b200_encoder_batch_write_header(enc, hdr.data());
+    }
+    ctx->pipelining = true;
+    std::vector<cudaEvent_t> events;
+    std::vector<uint64_t> pcm_off(n), out_off(n);
+    std::vector<uint32_t> chunk(n);
+    for (uint32_t f0 = 0, t = 0; f0 < max_frames && rc == 0; f0 += frames_per_chunk, ++t) {
+        cudaStream_t s = ctx->pipe_streams[t % 3];
+        uint64_t pcm_total = 0, out_total = 0;
+        for (size_t i = 0; i < n; ++i) {
+            chunk[i] = 0;
+            if (status[i] != QOA_B200_OK) continue;
+            const uint64_t done = (uint64_t)f0 * QOA_B200_FRAME_LEN;
+            if (done >= descs[i].samples) continue;
+            chunk[i] = (uint32_t)std::min<uint64_t>((uint64_t)frames_per_chunk * QOA_B200_FRAME_LEN, descs[i].samples - done);
+            pcm_off[i] = pcm_total;
+            pcm_total += ((uint64_t)chunk[i] * descs[i].channels + 7) & ~7ull;
+            out_off[i] = out_total;
+            out_total += (qoa_b200_encoded_size(descs[i].channels, chunk[i]) - QOA_B200_HEADER_SIZE + 15) & ~15ull;
+        }
+        int16_t *d_pcm = static_cast<int16_t *>(ctx->alloc((pcm_total + 8) * sizeof(int16_t)));
+        uint8_t *d_out = static_cast<uint8_t *>(ctx->alloc(out_total + 16));
+        if (!d_pcm || !d_out) {
+            ctx->err = "out of device memory (pipelined encode arenas)";
+            rc = QOA_B200_E_NOMEM;
+            break;
+        }
+        ctx->deferred.push_back(d_pcm);
+        ctx->deferred.push_back(d_out);
+        cudaError_t e = cudaSuccess;
+        for (size_t i = 0; i < n && e == cudaSuccess; ++i)
+            if (chunk[i])
+                e = cudaMemcpyAsync(d_pcm + pcm_off[i], pcm[i] + (uint64_t)f0 * QOA_B200_FRAME_LEN * descs[i].channels,
+                                    (uint64_t)chunk[i] * descs[i].channels * sizeof(int16_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && !events.empty()) e = cudaStreamWaitEvent(s, events.back(), 0); // LMS state order
+        if (e == cudaSuccess) {
+            rc = qoa_b200_encoder_batch_encode_chunk_dev(enc, d_pcm, pcm_off.data(), chunk.data(), d_out, out_off.data(), s);
+            if (rc != 0) break;
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) {
+                events.push_back(ev);
+                e = cudaEventRecord(ev, s);
+            }
+        }
+        for (size_t i = 0; i < n && e == cudaSuccess; ++i)
+            if (chunk[i]) {
+                const uint32_t ch = descs[i].channels;
+                const size_t dst = QOA_B200_HEADER_SIZE + (size_t)f0 * qoa_b200_frame_size(ch, QOA_B200_FRAME_LEN);
+                e = cudaMemcpyAsync(out[i] + dst, d_out + out_off[i], qoa_b200_encoded_size(ch, chunk[i]) - QOA_B200_HEADER_SIZE,
+                                    cudaMemcpyDeviceToHost, s);
+            }
+        if (e != cudaSuccess) {
+            ctx->err = std::string("pipelined encode: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            rc = QOA_B200_E_CUDA;
+        }
+    }
+    for (auto &ps : ctx->pipe_streams) {
+        cudaError_t e = cudaStreamSynchronize(ps);
+        if (e != cudaSuccess && rc == 0) {
+            ctx->err = std::string("pipelined encode: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            rc = QOA_B200_E_CUDA;
+        }
+    }
+    for (auto ev : events) cudaEventDestroy(ev);
+    ctx->pipelining = false;
+    for (void *p : ctx->deferred) ctx->release(p);
+    ctx->deferred.clear();
+    qoa_b200_encoder_batch_free(enc);
+    return rc;
 }
 
 // ================================================================================================================

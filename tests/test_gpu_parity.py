@@ -448,3 +448,29 @@ def test_decode_all_batch_pipelined(eng):
     infos2, outs2 = eng.decode_batch([s.tobytes() for s in streams[:12]], 1)
     for i in range(12):
         assert np.array_equal(outs[i][:infos2[i]["samples"]], outs2[i])
+
+
+def test_encode_all_batch_pipelined(eng, N):
+    """Host batches above 192 MB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
+    the device between chunks; the bytes must equal the one-shot result (= the oracle), invalid streams included."""
+    import torch
+    n_streams, ch, rate, n = 62, 2, 48000, 5120 * 160 + 777
+    pcm = torch.empty(n_streams * ch * n, dtype=torch.int16, device="cuda")
+    eng.gen_pcm_dev(pcm.data_ptr(), n_streams, 300, ch, n, 0, 2, "music")
+    host = pcm.cpu().numpy().reshape(n_streams, -1)
+    extra = [(1, 8000, 12345), (8, 96000, 5120 * 3 + 19), (3, 44100, 1)]
+    pcm_list = [host[i] for i in range(n_streams)] + [signals.synth_pcm(5, 900 + j, c, m) for j, (c, r, m) in enumerate(extra)]
+    descs = [(ch, rate, n)] * n_streams + extra
+    pcm_list.append(np.zeros(10, np.int16))
+    descs.append((2, 0, 5))  # InvalidSampleRate in the middle of a pipelined batch
+    assert sum(p.size for p in pcm_list) >= 96 << 20
+    st, outs = eng.encode_all_batch(pcm_list, descs)
+    assert st == [0] * (n_streams + len(extra)) + [N.ENC_INVALID_SAMPLE_RATE]
+    rc, ref = ob.mt_encode(host.reshape(-1), n_streams, ch, rate, n, 16)
+    assert rc == 0
+    size = ob.encoded_size(ch, n)
+    ref = ref.reshape(n_streams, size)
+    for i in range(n_streams):
+        assert outs[i].size == size and np.array_equal(outs[i], ref[i]), i
+    for j, d in enumerate(extra):
+        assert outs[n_streams + j].tobytes() == ob.encode_all(pcm_list[n_streams + j], *d)[1], d
