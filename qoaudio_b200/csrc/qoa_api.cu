@@ -9,6 +9,7 @@
 // entry point fails with QOA_B200_E_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -151,6 +152,60 @@ struct Scratch {
         return static_cast<T *>(p);
     }
 };
+
+// ---- batched host <-> device copies ---------------------------------------------------------------------------------
+// Items whose host side is pinned (device-accessible through UVA) and 16-byte aligned are moved by ONE kernel
+// (launch_copy_items); the rest fall back to one cudaMemcpyAsync each.  `host_is_src` tells which side is the host's.
+namespace {
+
+bool device_accessible(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) &&
+           a.devicePointer != nullptr;
+}
+
+// `known` (optional, one entry per item): 1 = the host side is known to be device-accessible, 0 = known not to be;
+// without it every item's host pointer is queried (cudaPointerGetAttributes, ~1 us each).
+int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &items, bool host_is_src, cudaStream_t s,
+               const std::vector<char> *known = nullptr)
+{
+    std::vector<CopyItem> fast;
+    uint64_t max_bytes = 0;
+    static const bool enabled = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0); // development aid
+    const bool many = enabled && items.size() >= 32; // a handful of copies is cheaper through the copy engines
+    for (size_t k = 0; k < items.size(); ++k) {
+        const CopyItem &it = items[k];
+        if (it.bytes == 0) continue;
+        const void *host = host_is_src ? it.src : it.dst;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 15) == 0;
+        // SM copies over PCIe reach ~22 GB/s against ~55 GB/s for the copy engines, a cudaMemcpyAsync call costs ~4 us:
+        // the kernel wins below ~256 KB per buffer
+        if (many && aligned && it.bytes < (256u << 10) && (known ? (*known)[k] != 0 : device_accessible(host))) {
+            fast.push_back(it);
+            max_bytes = std::max(max_bytes, it.bytes);
+        } else {
+            CHECK_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.bytes, host_is_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s));
+        }
+    }
+    if (!fast.empty()) {
+        CopyItem *d_items = sc.get<CopyItem>(fast.size());
+        if (!d_items) {
+            ctx->err = "out of device memory (copy table)";
+            return QOA_B200_E_NOMEM;
+        }
+        CHECK_CUDA(ctx, cudaMemcpyAsync(d_items, fast.data(), fast.size() * sizeof(CopyItem), cudaMemcpyHostToDevice, s));
+        CHECK_CUDA(ctx, launch_copy_items(d_items, (uint32_t)fast.size(), max_bytes, s));
+        ctx->launches += 1;
+    }
+    return 0;
+}
+
+} // namespace
 
 extern "C" {
 
@@ -334,9 +389,15 @@ extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc 
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     {
-        uint64_t total = 0;
-        for (size_t i = 0; i < n; ++i) total += pcm_len[i];
-        if (total >= (96ull << 20)) // >= 192 MB of PCM: overlap the copies with the kernel, chunked in time
+        // >= 1 GB of PCM: overlap the copies with the kernel in time chunks of ~512 MB (at least two frames of every
+        // stream per chunk so that per-chunk table uploads and launches stay small next to the chunk's kernel;
+        // per-stream copies are batched into one kernel when the host buffers are pinned).
+        uint64_t total = 0, per_frame_step = 0;
+        for (size_t i = 0; i < n; ++i) {
+            total += pcm_len[i];
+            if (validate_desc(descs[i]) == QOA_B200_OK) per_frame_step += (uint64_t)QOA_B200_FRAME_LEN * descs[i].channels;
+        }
+        if (total >= (512ull << 20) && per_frame_step && (256ull << 20) / per_frame_step >= 2)
             return encode_all_batch_pipelined(ctx, descs, pcm, pcm_len, out, out_cap, out_len, status, n, total);
     }
     cudaStream_t s = nullptr;
@@ -365,15 +426,19 @@ extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc 
             ctx->err = "out of device memory (encode arenas)";
             return QOA_B200_E_NOMEM;
         }
+        std::vector<CopyItem> items;
         for (size_t i = 0; i < n; ++i)
-            if (caps[i])
-                CHECK_CUDA(ctx, cudaMemcpyAsync(d_pcm + pcm_off[i], pcm[i], pcm_len[i] * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+            if (caps[i]) items.push_back({pcm[i], d_pcm + pcm_off[i], pcm_len[i] * sizeof(int16_t)});
+        rc = copy_batch(ctx, sc, items, true, s);
+        if (rc != 0) return rc;
         rc = qoa_b200_encode_all_batch_dev(ctx, descs, d_pcm, pcm_off.data(), pcm_len, d_out, out_off.data(), caps.data(),
                                            out_len, status, n, s);
         if (rc != 0) return rc;
+        items.clear();
         for (size_t i = 0; i < n; ++i)
-            if (status[i] == QOA_B200_OK && out_len[i])
-                CHECK_CUDA(ctx, cudaMemcpyAsync(out[i], d_out + out_off[i], out_len[i], cudaMemcpyDeviceToHost, s));
+            if (status[i] == QOA_B200_OK && out_len[i]) items.push_back({d_out + out_off[i], out[i], out_len[i]});
+        rc = copy_batch(ctx, sc, items, false, s);
+        if (rc != 0) return rc;
         CHECK_CUDA(ctx, cudaStreamSynchronize(s));
     }
     return 0;
@@ -608,7 +673,7 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
     }
     if (values_per_frame_step == 0) return 0;
     (void)total_pcm_values;
-    const uint32_t frames_per_chunk = (uint32_t)std::max<uint64_t>(1, (48ull << 20) / values_per_frame_step); // ~96 MB of PCM
+    const uint32_t frames_per_chunk = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / values_per_frame_step); // ~512 MB of PCM
     qoa_b200_encoder_batch *enc = nullptr;
     std::vector<int32_t> new_status(n);
     int rc = qoa_b200_encoder_batch_new(ctx, d.data(), n, new_status.data(), &enc);
@@ -623,6 +688,13 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
     std::vector<cudaEvent_t> events;
     std::vector<uint64_t> pcm_off(n), out_off(n);
     std::vector<uint32_t> chunk(n);
+    std::vector<char> pcm_pinned(n, 0), out_pinned(n, 0), known;
+    if (n >= 32)
+        for (size_t i = 0; i < n; ++i)
+            if (status[i] == QOA_B200_OK) {
+                pcm_pinned[i] = device_accessible(pcm[i]);
+                out_pinned[i] = device_accessible(out[i]);
+            }
     for (uint32_t f0 = 0, t = 0; f0 < max_frames && rc == 0; f0 += frames_per_chunk, ++t) {
         cudaStream_t s = ctx->pipe_streams[t % 3];
         uint64_t pcm_total = 0, out_total = 0;
@@ -647,10 +719,17 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
         ctx->deferred.push_back(d_pcm);
         ctx->deferred.push_back(d_out);
         cudaError_t e = cudaSuccess;
-        for (size_t i = 0; i < n && e == cudaSuccess; ++i)
-            if (chunk[i])
-                e = cudaMemcpyAsync(d_pcm + pcm_off[i], pcm[i] + (uint64_t)f0 * QOA_B200_FRAME_LEN * descs[i].channels,
-                                    (uint64_t)chunk[i] * descs[i].channels * sizeof(int16_t), cudaMemcpyHostToDevice, s);
+        Scratch sc(ctx);
+        std::vector<CopyItem> items;
+        known.clear();
+        for (size_t i = 0; i < n; ++i)
+            if (chunk[i]) {
+                items.push_back({pcm[i] + (uint64_t)f0 * QOA_B200_FRAME_LEN * descs[i].channels, d_pcm + pcm_off[i],
+                                 (uint64_t)chunk[i] * descs[i].channels * sizeof(int16_t)});
+                known.push_back(pcm_pinned[i]);
+            }
+        rc = copy_batch(ctx, sc, items, true, s, &known);
+        if (rc != 0) break;
         if (e == cudaSuccess && !events.empty()) e = cudaStreamWaitEvent(s, events.back(), 0); // LMS state order
         if (e == cudaSuccess) {
             rc = qoa_b200_encoder_batch_encode_chunk_dev(enc, d_pcm, pcm_off.data(), chunk.data(), d_out, out_off.data(), s);
@@ -662,13 +741,19 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
                 e = cudaEventRecord(ev, s);
             }
         }
-        for (size_t i = 0; i < n && e == cudaSuccess; ++i)
+        items.clear();
+        known.clear();
+        for (size_t i = 0; i < n; ++i)
             if (chunk[i]) {
                 const uint32_t ch = descs[i].channels;
                 const size_t dst = QOA_B200_HEADER_SIZE + (size_t)f0 * qoa_b200_frame_size(ch, QOA_B200_FRAME_LEN);
-                e = cudaMemcpyAsync(out[i] + dst, d_out + out_off[i], qoa_b200_encoded_size(ch, chunk[i]) - QOA_B200_HEADER_SIZE,
-                                    cudaMemcpyDeviceToHost, s);
+                items.push_back({d_out + out_off[i], out[i] + dst, qoa_b200_encoded_size(ch, chunk[i]) - QOA_B200_HEADER_SIZE});
+                known.push_back(out_pinned[i]);
             }
+        if (e == cudaSuccess) {
+            rc = copy_batch(ctx, sc, items, false, s, &known);
+            if (rc != 0) break;
+        }
         if (e != cudaSuccess) {
             ctx->err = std::string("pipelined encode: ") + cudaGetErrorString(e);
             cudaGetLastError();
@@ -846,16 +931,17 @@ static int plan_create_host(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const 
         ctx->err = "out of device memory (input arena)";
         return QOA_B200_E_NOMEM;
     }
-    for (size_t i = 0; i < n; ++i)
-        if (len[i]) {
-            cudaError_t e = cudaMemcpyAsync(arena + off[i], qoa[i], len[i], cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) {
-                ctx->err = std::string("H2D input copy: ") + cudaGetErrorString(e);
-                cudaGetLastError();
-                ctx->release(arena);
-                return QOA_B200_E_CUDA;
-            }
+    {
+        Scratch sc(ctx);
+        std::vector<CopyItem> items;
+        for (size_t i = 0; i < n; ++i)
+            if (len[i]) items.push_back({qoa[i], arena + off[i], len[i]});
+        int rcc = copy_batch(ctx, sc, items, true, s);
+        if (rcc != 0) {
+            ctx->release(arena);
+            return rcc;
         }
+    }
     int rc = qoa_b200_decode_plan_create_dev(ctx, arena, off.data(), len, n, mode, s, out);
     if (rc != 0) {
         ctx->release(arena);
@@ -984,15 +1070,15 @@ static int plan_run_host(qoa_b200_decode_plan *plan, int16_t *const *out, const 
     }
     int rc = qoa_b200_decode_plan_run_dev(plan, d_out, off.data(), out_cap, status, s);
     if (rc == 0) {
-        for (size_t i = 0; i < n && rc == 0; ++i) {
-            const uint64_t cnt = plan->info[i].samples;
-            if (cnt == 0 || cnt > out_cap[i] || !out[i]) continue;
-            cudaError_t e = cudaMemcpyAsync(out[i], d_out + off[i], cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, s);
-            if (e != cudaSuccess) {
-                ctx->err = std::string("D2H output copy: ") + cudaGetErrorString(e);
-                cudaGetLastError();
-                rc = QOA_B200_E_CUDA;
+        {
+            Scratch sc(ctx);
+            std::vector<CopyItem> items;
+            for (size_t i = 0; i < n; ++i) {
+                const uint64_t cnt = plan->info[i].samples;
+                if (cnt == 0 || cnt > out_cap[i] || !out[i]) continue;
+                items.push_back({d_out + off[i], out[i], cnt * sizeof(int16_t)});
             }
+            rc = copy_batch(ctx, sc, items, false, s);
         }
         cudaError_t e = sync ? cudaStreamSynchronize(s) : cudaSuccess;
         if (e != cudaSuccess && rc == 0) {

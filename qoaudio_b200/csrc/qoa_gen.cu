@@ -92,6 +92,44 @@ cudaError_t launch_gen_qoa(uint8_t *d_qoa, uint64_t stride, uint64_t n_streams, 
     return cudaGetLastError();
 }
 
+// ---- batched host <-> device copies through mapped pinned memory -------------------------------------------------
+// A batch of thousands of per-stream buffers costs one cudaMemcpyAsync call each (~4 us) — more than the transfer for
+// streams of a few hundred KB.  When the caller's buffers are pinned (device-accessible), ONE kernel moves them all:
+// block (item, tile) copies a 64 KB tile with 16-byte accesses straight over PCIe.
+constexpr uint32_t kCopyTile = 64 * 1024;
+
+__global__ void __launch_bounds__(256) copy_items_kernel(const CopyItem *__restrict__ items)
+{
+    const CopyItem it = items[blockIdx.x];
+    const uint64_t t0 = (uint64_t)blockIdx.y * kCopyTile;
+    if (t0 >= it.bytes) return;
+    const uint64_t len = min((uint64_t)kCopyTile, it.bytes - t0);
+    const uint8_t *src = static_cast<const uint8_t *>(it.src) + t0;
+    uint8_t *dst = static_cast<uint8_t *>(it.dst) + t0;
+    const uint32_t nvec = (uint32_t)(len / 16);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint32_t i = threadIdx.x;
+    for (; i + 3 * 256 < nvec; i += 4 * 256) { // four loads in flight per thread
+        const uint4 a = s4[i], b = s4[i + 256], c = s4[i + 512], d = s4[i + 768];
+        d4[i] = a;
+        d4[i + 256] = b;
+        d4[i + 512] = c;
+        d4[i + 768] = d;
+    }
+    for (; i < nvec; i += 256) d4[i] = s4[i];
+    for (uint32_t b = nvec * 16 + threadIdx.x; b < len; b += 256) dst[b] = src[b];
+}
+
+cudaError_t launch_copy_items(const CopyItem *d_items, uint32_t n_items, uint64_t max_bytes, cudaStream_t s)
+{
+    if (n_items == 0 || max_bytes == 0) return cudaSuccess;
+    const uint64_t tiles = (max_bytes + kCopyTile - 1) / kCopyTile;
+    if (tiles > 65535) return cudaErrorInvalidConfiguration;
+    copy_items_kernel<<<dim3(n_items, (unsigned)tiles), 256, 0, s>>>(d_items);
+    return cudaGetLastError();
+}
+
 // ---- integer issue-rate microbenchmark -----------------------------------------------------------------------
 // 8 independent dependency chains per thread, 16 warps per SM x 4 CTAs: enough to saturate every scheduler.
 // kind 0 = IMAD, 1 = LOP3, 2 = IMAD + LOP3 1:1 (the two-pipe issue peak).  Kinds >= 3 time single SASS opcodes the

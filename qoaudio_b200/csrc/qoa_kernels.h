@@ -57,6 +57,15 @@ struct EncChain {
 cudaError_t launch_encode(const int16_t *d_pcm, uint8_t *d_out, const EncJob *d_jobs, const EncChain *d_chains,
                           uint32_t n_chains, int32_t *d_lms, cudaStream_t s, int *n_launches);
 
+// ---- batched copies -------------------------------------------------------------------------------------------
+// One kernel copies n_items buffers (src/dst 16-byte aligned, device-accessible: device memory or pinned host memory).
+struct CopyItem {
+    const void *src;
+    void *dst;
+    uint64_t bytes;
+};
+cudaError_t launch_copy_items(const CopyItem *d_items, uint32_t n_items, uint64_t max_bytes, cudaStream_t s);
+
 // ---- generators / microbenchmarks ----------------------------------------------------------------------------
 cudaError_t launch_gen_pcm(int16_t *d_pcm, uint64_t n_streams, uint64_t first_stream, uint32_t channels,
                            uint64_t samples, uint64_t start, uint64_t seed, int kind, cudaStream_t s);

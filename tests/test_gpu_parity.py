@@ -451,10 +451,10 @@ def test_decode_all_batch_pipelined(eng):
 
 
 def test_encode_all_batch_pipelined(eng, N):
-    """Host batches above 192 MB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
+    """Host batches above 1 GB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
     the device between chunks; the bytes must equal the one-shot result (= the oracle), invalid streams included."""
     import torch
-    n_streams, ch, rate, n = 62, 2, 48000, 5120 * 160 + 777
+    n_streams, ch, rate, n = 62, 2, 48000, 5120 * 850 + 777
     pcm = torch.empty(n_streams * ch * n, dtype=torch.int16, device="cuda")
     eng.gen_pcm_dev(pcm.data_ptr(), n_streams, 300, ch, n, 0, 2, "music")
     host = pcm.cpu().numpy().reshape(n_streams, -1)
@@ -463,7 +463,7 @@ def test_encode_all_batch_pipelined(eng, N):
     descs = [(ch, rate, n)] * n_streams + extra
     pcm_list.append(np.zeros(10, np.int16))
     descs.append((2, 0, 5))  # InvalidSampleRate in the middle of a pipelined batch
-    assert sum(p.size for p in pcm_list) >= 96 << 20
+    assert sum(p.size for p in pcm_list) >= 512 << 20
     st, outs = eng.encode_all_batch(pcm_list, descs)
     assert st == [0] * (n_streams + len(extra)) + [N.ENC_INVALID_SAMPLE_RATE]
     rc, ref = ob.mt_encode(host.reshape(-1), n_streams, ch, rate, n, 16)
