@@ -96,7 +96,7 @@ def cpu_reference(args, want_encode=True):
     threads = cores
     # ---- decode sample: real encoder output of `threads` distinct 60 s streams would cost minutes of CPU encode;
     # decode cost is data-independent, so the sample is built like the GPU's generator: valid headers + random payload.
-    n_dec = max(256, threads * 2)  # ~20 core-seconds of CPU work
+    n_dec = max(512, threads * 2)  # ~18 core-seconds of CPU work
     size = enc_size(DEC_CH, DEC_SAMPLES)
     rng = np.random.default_rng(1)
     proto = np.frombuffer(rng.bytes(size), dtype=np.uint8).copy()
@@ -157,7 +157,7 @@ def run_reference(args):
     dec["value"] = v
     line = {"impl": "reference", "metric": "batch decode throughput", "value": v, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": len(vals), "warmup": warm,
-            "ms_per_step": DEC_SAMPLES * DEC_CH * max(256, 2 * (os.cpu_count() or 1)) / v / 1e3, "higher_is_better": True,
+            "ms_per_step": DEC_SAMPLES * DEC_CH * max(512, 2 * (os.cpu_count() or 1)) / v / 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": workload_config(args), "cpu_baseline": dec,
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
