@@ -6,8 +6,9 @@
 //   decode_one_slice_per_channel          :291-330   the 20-sample LMS loop
 //   Iterator::next                        :661-693   item order, streaming-mode dummy header
 //   decode_all                            :713-747   extra IncompatibleFrame check
-// Every frame header carries its own LMS state (:270-281), so frames decode independently: one thread owns one
-// (frame, channel pair) and walks its slices; nothing crosses a frame.
+// Every frame header carries its own LMS state (:270-281), so frames decode independently: one thread owns one frame
+// (mono / stereo fast path), one (frame, channel pair) or one (frame, channel) and walks its slices; nothing crosses a
+// frame.
 #include <cuda.h>
 
 #include <algorithm>
@@ -473,11 +474,13 @@ struct SingleLoop<20> {
 // stereo), so direct per-lane stores would cost one L1 wavefront per lane per instruction.  Instead every lane stages
 // S slices (240 B of PCM: S = 3 stereo, S = 6 mono) in its own row of a per-warp shared-memory tile [32 lanes][240 B]
 // and the tile goes to global memory through the TMA engine:
-//   * regular warps (32 consecutive full frames of one stream, i.e. rows exactly one frame of PCM apart in the
-//     output): ONE 2-D tensor store per warp per group (cp.async.bulk.tensor.2d, box = 60 words x 32 rows of a tensor
-//     map that views the output arena as rows of one frame of PCM) — no copy-out instructions at all;
-//   * everything else (warps that straddle two streams, short last frames, partial slices; ~8 % of the groups):
-//     the warp copies the tile row by row with 16-byte shared loads / global stores, one half-warp per 240-byte row.
+//   * regular boxes (8 consecutive full frames of one stream, i.e. rows exactly one frame of PCM apart in the
+//     output): one 2-D tensor store per box per group (cp.async.bulk.tensor.2d, box = 60 words x 8 rows of a tensor
+//     map that views the output arena as rows of one frame of PCM, dim 0 extended by one box so that a box may start
+//     anywhere in a row) — no copy-out instructions at all; the last, shorter group of a frame (256 mod S slices) is
+//     staged densely and leaves through a second map with a narrower box;
+//   * everything else (the box that contains a stream boundary, short last frames, partial slices; 1-2 % of the
+//     rows): the warp copies those rows with 16-byte shared loads / global stores, one half-warp per 240-byte row.
 //     (Measured alternatives: per-lane cp.async.bulk copies — UBLKCP takes uniform operands, so the compiler
 //     serialises it over the 32 lanes, ~480 instructions per group; per-lane 16-byte stores — 32 scattered sectors
 //     per instruction, groups on that path ran 1.8x slower.)
@@ -738,11 +741,11 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
 }
 
 // Encodes the tensor map that views the output arena as rows of `row_bytes` (the PCM of one full frame) of 32-bit words;
-// box = box_words x box_rows.  Returns 0 when the driver entry point is unavailable or the arena does not qualify
-// (the kernel then uses per-lane bulk copies only).
-// Returns 0 when no map could be made, 2 when the map's rows overlap (dim 0 is extended by one box beyond the row pitch,
+// box = box_words x box_rows.
+// Returns 0 when no map could be made (driver entry point unavailable, arena not 16-byte aligned: the kernel then
+// copies every row itself), 2 when the map's rows overlap (dim 0 is extended by one box beyond the row pitch,
 // so a box may start anywhere in a row and run into the next one), 1 when the driver refused overlapping rows (boxes
-// that would cross a row end are then left to the per-lane copy path).
+// that would cross a row end are then left to the row copy path).
 static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint32_t box_words, uint32_t row_bytes,
                         uint32_t box_rows)
 {

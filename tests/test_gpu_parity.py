@@ -105,9 +105,9 @@ def test_edge_signals_all_channel_counts(eng):
 
 # ---- config 5: mixed batch --------------------------------------------------------------------------------------------
 
-def mixed_batch(count=64, seed=1, long_every=16):
+def mixed_batch(count=256, seed=1, long_every=16):
     rates = [8000, 11025, 16000, 22050, 32000, 44100, 48000, 96000]
-    lengths = [1, 19, 20, 21, 39, 40, 41, 5119, 5120, 5121, 10259, 12345]
+    lengths = [1, 19, 20, 21, 39, 40, 41, 5119, 5120, 5121, 10259, 12345]  # + 123457 / ch and rate * 7 + 13 below
     pcm_list, descs = [], []
     for i in range(count):
         ch = i % 8 + 1
@@ -115,6 +115,8 @@ def mixed_batch(count=64, seed=1, long_every=16):
         n = lengths[(i * 7 + i // 8) % len(lengths)]
         if long_every and i % long_every == long_every - 1:
             n = 123457 // ch
+        elif long_every and i % long_every == 7:
+            n = (rate * 7 + 13) // (8 if rate > 16000 else 1)
         kind = "noise" if i % 5 == 4 else "music"
         pcm_list.append(signals.synth_pcm(seed, i, ch, n, kind))
         descs.append((ch, rate, n))
@@ -122,7 +124,9 @@ def mixed_batch(count=64, seed=1, long_every=16):
 
 
 def test_mixed_batch_roundtrip(eng):
+    """BASELINE.json configs[4]: 256 mixed streams, 1-8 channels, 8-96 kHz, odd lengths with partial frames/slices."""
     pcm_list, descs = mixed_batch()
+    assert len(descs) == 256 and {d[0] for d in descs} == set(range(1, 9))
     st, outs = eng.encode_all_batch(pcm_list, descs)
     assert st == [0] * len(descs)
     enc = []
