@@ -788,10 +788,15 @@ struct qoa_b200_decode_plan {
     uint8_t *owned_arena = nullptr;
     FrameRec *d_recs = nullptr;
     uint64_t n_frames = 0;
-    uint32_t max_ch = 0;
-    uint32_t uniform_ch = 0; // 1 / 2: every indexed frame is mono / stereo and 16-byte aligned in the output
     std::vector<qoa_b200_stream_info> info;
-    std::vector<uint64_t> frame_base; // n + 1
+    std::vector<uint64_t> frame_base; // first FrameRec of stream i
+    // The frame table is grouped by kernel class so that a mixed batch still runs every stream on its fast kernel:
+    // class c = 1..8: streams whose frames all have c channels and start 16-byte aligned in the output;
+    // class 0: everything else (per-frame channel changes, > 8 channels, odd-sized interior frames) -> generic kernel.
+    std::vector<uint8_t> cls;       // class of stream i
+    std::vector<size_t> order;      // stream indices in table order (class 1..8, then 0)
+    uint64_t cls_start[9] = {0}, cls_frames[9] = {0};
+    uint32_t cls_max_ch[9] = {0};
 };
 
 namespace {
@@ -821,35 +826,43 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
     ctx->launches += 1;
     CHECK_CUDA(ctx, cudaStreamSynchronize(s));
     plan->info.assign(h_info, h_info + n);
-    plan->frame_base.assign(n + 1, 0);
-    uint32_t max_ch = 0, max_regular_frames = 0;
+    plan->frame_base.assign(n, 0);
+    plan->cls.assign(n, 0);
+    plan->order.clear();
+    uint32_t max_regular_frames = 0;
     size_t n_regular = 0;
-    bool uniform = true;
-    uint32_t first_ch = 0;
+    for (int c = 0; c < 9; ++c) plan->cls_start[c] = plan->cls_frames[c] = plan->cls_max_ch[c] = 0;
     for (size_t i = 0; i < n; ++i) {
         const auto &inf = plan->info[i];
-        plan->frame_base[i + 1] = plan->frame_base[i] + inf.index_frames;
         if (inf.flags & QOA_B200_INFO_REGULAR) {
             ++n_regular;
             max_regular_frames = std::max(max_regular_frames, inf.index_frames);
         }
-        if (inf.index_frames) {
-            max_ch = std::max(max_ch, inf.max_channels);
-            if (!first_ch) first_ch = inf.max_channels;
-            if (inf.max_channels != first_ch || !(inf.flags & QOA_B200_INFO_UNIFORM_CH) || !(inf.flags & QOA_B200_INFO_ALIGNED16))
-                uniform = false;
-        }
+        const bool fast = inf.index_frames && inf.max_channels >= 1 && inf.max_channels <= 8 &&
+                          (inf.flags & QOA_B200_INFO_UNIFORM_CH) && (inf.flags & QOA_B200_INFO_ALIGNED16);
+        plan->cls[i] = fast ? (uint8_t)inf.max_channels : 0;
     }
-    plan->n_frames = plan->frame_base[n];
-    plan->max_ch = max_ch;
-    plan->uniform_ch = (uniform && plan->n_frames > 0 && first_ch >= 1 && first_ch <= 8) ? first_ch : 0;
+    uint64_t next = 0;
+    static const int kClassOrder[9] = {1, 2, 3, 4, 5, 6, 7, 8, 0};
+    for (int c : kClassOrder) {
+        plan->cls_start[c] = next;
+        for (size_t i = 0; i < n; ++i)
+            if (plan->cls[i] == c) {
+                plan->frame_base[i] = next;
+                next += plan->info[i].index_frames;
+                plan->order.push_back(i);
+                plan->cls_max_ch[c] = std::max(plan->cls_max_ch[c], plan->info[i].max_channels);
+            }
+        plan->cls_frames[c] = next - plan->cls_start[c];
+    }
+    plan->n_frames = next;
     if (plan->n_frames) {
         if (!plan->d_recs) plan->d_recs = static_cast<FrameRec *>(ctx->alloc(plan->n_frames * sizeof(FrameRec)));
         if (!plan->d_recs) {
             ctx->err = "out of device memory (frame index)";
             return QOA_B200_E_NOMEM;
         }
-        CHECK_CUDA(ctx, cudaMemcpyAsync(d_fbase, plan->frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        CHECK_CUDA(ctx, cudaMemcpyAsync(d_fbase, plan->frame_base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         if (n_regular < n) {
             CHECK_CUDA(ctx, launch_index_fill(plan->d_arena, d_off, d_len, n, plan->mode, d_info, d_fbase, plan->d_recs, s));
             ctx->launches += 1;
@@ -976,8 +989,8 @@ extern "C" size_t qoa_b200_decode_plan_frame_headers(const qoa_b200_decode_plan 
                                                      qoa_b200_frame_header *hdrs, size_t cap)
 {
     if (!plan || i >= plan->n) return 0;
-    const uint64_t f0 = plan->frame_base[i], f1 = plan->frame_base[i + 1];
-    const size_t count = (size_t)(f1 - f0);
+    const uint64_t f0 = plan->frame_base[i];
+    const size_t count = plan->info[i].index_frames;
     const size_t m = std::min(count, cap);
     if (m && hdrs) {
         std::vector<FrameRec> recs(m);
@@ -1012,7 +1025,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     ctx->enter(s);
     Scratch sc(ctx);
     std::vector<uint64_t> base(n);
-    bool aligned = true;
+    bool cls_aligned[9] = {true, true, true, true, true, true, true, true, true};
     uint64_t out_bytes = 0;
     for (size_t i = 0; i < n; ++i) {
         int st = plan->info[i].status;
@@ -1021,7 +1034,7 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
             base[i] = ~0ull;
         } else {
             base[i] = out_off[i];
-            if (out_off[i] & 7) aligned = false;
+            if (out_off[i] & 7) cls_aligned[plan->cls[i]] = false;
             out_bytes = std::max<uint64_t>(out_bytes, (out_off[i] + plan->info[i].samples) * 2);
         }
         if (status) status[i] = st;
@@ -1033,10 +1046,14 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
         return QOA_B200_E_NOMEM;
     }
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_base, base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    int nl = 0;
-    CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs, plan->n_frames, plan->max_ch, aligned ? plan->uniform_ch : 0u,
-                                  d_base, d_out, out_bytes, s, &nl));
-    ctx->launches += nl;
+    for (int c = 0; c < 9; ++c) { // one launch per kernel class present in the batch
+        if (!plan->cls_frames[c]) continue;
+        int nl = 0;
+        CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs + plan->cls_start[c], plan->cls_frames[c],
+                                      plan->cls_max_ch[c], (c && cls_aligned[c]) ? (uint32_t)c : 0u, d_base, d_out, out_bytes,
+                                      s, &nl));
+        ctx->launches += nl;
+    }
     return 0;
 }
 
@@ -1055,13 +1072,14 @@ static int plan_run_host(qoa_b200_decode_plan *plan, int16_t *const *out, const 
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint64_t> off(n, 0);
     uint64_t total = 0;
-    // Every stream gets a slot that starts on a multiple of one full frame of PCM (5120 x channels values) when the
-    // batch takes the mono / stereo fast path: frames of consecutive streams then stay on the 2-D tensor map's row
-    // lattice, so boxes that span a stream boundary still leave through one tensor store (measured: +4 %).
-    const uint64_t slot = (plan->uniform_ch == 1 || plan->uniform_ch == 2) ? (uint64_t)QOA_B200_FRAME_LEN * plan->uniform_ch : 8;
-    for (size_t i = 0; i < n; ++i) {
+    // The arena follows the frame table's order (grouped by kernel class).  Mono / stereo streams get slots that start
+    // on a multiple of one full frame of PCM (5120 x channels values): frames of consecutive streams then stay on the
+    // 2-D tensor map's row lattice, so boxes that span a stream boundary still leave through one tensor store (+4 %).
+    for (size_t i : plan->order) {
+        const uint64_t slot = (plan->cls[i] == 1 || plan->cls[i] == 2) ? (uint64_t)QOA_B200_FRAME_LEN * plan->cls[i] : 8;
+        total = (total + slot - 1) / slot * slot;
         off[i] = total;
-        if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + slot - 1) / slot * slot;
+        if (plan->info[i].samples <= out_cap[i]) total += (plan->info[i].samples + 7) & ~7ull;
     }
     int16_t *d_out = static_cast<int16_t *>(ctx->alloc((total + 8) * sizeof(int16_t)));
     if (!d_out) {

@@ -393,6 +393,48 @@ def test_gen_qoa_decodes_like_oracle(eng):
     plan.close()
 
 
+def test_mixed_classes_device_offsets(eng):
+    """A shuffled batch of mono / stereo / 5.1 / channel-switching streams: the plan groups the frame table by kernel
+    class and launches each class on its own range.  Device-resident API with caller-chosen output offsets; one mono
+    slot is deliberately not 16-byte aligned, which sends only the mono class through the generic kernel."""
+    import torch
+    rng = np.random.default_rng(11)
+    streams, expect = [], []
+    for i in range(48):
+        ch = (1, 2, 6, 2, 1, 3)[i % 6]
+        n = int(rng.integers(1, 5120 * 4))
+        pcm = signals.synth_pcm(12, i, ch, n, "noise" if i % 7 == 3 else "music")
+        e = ob.encode_all(pcm, ch, 32000, n)[1]
+        if i % 12 == 5:  # stereo frames followed by mono frames in one stream (the iterator re-reads channels per frame)
+            m = ob.encode_all(signals.synth_pcm(13, i, 1, 6000), 1, 32000, 6000)[1]
+            e = e[:4] + bytes(4) + e[8:] + m[8:]  # streaming header: the channel switch is legal
+        streams.append(e)
+        expect.append(ob.decode_iter(e))
+    sizes = [len(s) for s in streams]
+    in_off = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).astype(np.uint64)
+    arena = np.zeros(int(in_off[-1]), dtype=np.uint8)
+    for o, s in zip(in_off, streams):
+        arena[int(o):int(o) + len(s)] = np.frombuffer(s, dtype=np.uint8)
+    d_arena = torch.from_numpy(arena).cuda()
+    for misalign in (0, 3):
+        caps = [len(x[1]) for x in expect]
+        out_off, total = [], 0
+        for i, c in enumerate(caps):
+            total = (total + 7) // 8 * 8 + (misalign if i == 6 else 0)
+            out_off.append(total)
+            total += c
+        out = torch.full((total + 8,), -21846, dtype=torch.int16, device="cuda")
+        plan = eng.decode_plan_dev(d_arena.data_ptr(), in_off[:-1], sizes, 0)
+        st = plan.run_dev(out.data_ptr(), out_off, caps)
+        torch.cuda.synchronize()
+        host = out.cpu().numpy()
+        for i, (oi, opcm, _) in enumerate(expect):
+            assert st[i] == oi["status"], (i, st[i], oi)
+            assert {k: plan.info[i][k] for k in INFO_KEYS} == oi, i
+            assert np.array_equal(host[out_off[i]:out_off[i] + caps[i]], opcm), (i, misalign)
+        plan.close()
+
+
 def test_device_encode_chunked_equals_one_shot(eng):
     """Time-chunked device-resident encode with persistent LMS state (the config-4 path) == encode_all."""
     import torch
