@@ -198,6 +198,9 @@ def main():
     torch.cuda.set_device(local)
     import qoaudio_b200 as q
     from qoaudio_b200.dist import Group
+    from qoaudio_b200 import hostbind
+    # pinned staging buffers of the e2e legs should live on the NUMA node next to this rank's GPU
+    cpus_before, cpus_bound = hostbind.bind_to_gpu(local)
     dev = torch.device("cuda", local)
     grp = Group(device=dev)  # NCCL when WORLD_SIZE > 1: barrier + max/sum of timings only, no data-path collective
     eng = q.Engine(local)
@@ -446,6 +449,7 @@ def main():
 
     cpu = cpu_enc = None
     if not args.no_cpu:
+        hostbind.restore(cpus_before)  # the CPU baseline gets every host core
         cpu, cpu_enc = cpu_reference(args, want_encode=not args.no_encode)
         if encode is not None:
             encode["cpu_baseline"] = cpu_enc
@@ -474,6 +478,9 @@ def main():
                              "(tools/hbm_probe.py), i.e. a workload ceiling of ~0.72 of the copy peak"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         "encode": encode, "single_stream": single,
+        "host_affinity": {"bound_cpus": len(cpus_bound) if cpus_bound else None, "allowed_cpus": len(cpus_before),
+                          "note": "rank bound to its GPU's NUMA-local CPUs before pinned buffers are allocated; null = "
+                                  "NVML reports no locality narrower than the allowed set (single-node host or VM)"},
     }
     print(json.dumps(line))
     grp.close()

@@ -134,7 +134,8 @@ cudaError_t launch_copy_items(const CopyItem *d_items, uint32_t n_items, uint64_
 // 8 independent dependency chains per thread, 16 warps per SM x 4 CTAs: enough to saturate every scheduler.
 // kind 0 = IMAD, 1 = LOP3, 2 = IMAD + LOP3 1:1 (the two-pipe issue peak).  Kinds >= 3 time single SASS opcodes the
 // kernels lean on (development aid): 3 I2IP.SAT, 4 VIMNMX, 5 SHF, 6 PRMT, 7 LEA.HI, 8 IMAD.HI, 9 IADD3, 10 SEL-free
-// ISETP+SEL pair, 11 IMAD.WIDE.
+// ISETP+SEL pair, 11 IMAD.WIDE, 12 IMAD imm, 13 IMUL, 14 LOP3 imm, 15 SHF one-register, 16 OR imm, 17 IADD3 three-register,
+// 18 IMAD + one-register SHF 1:1, 19 IMAD : LOP3 : SHF 2:1:1.
 #define QOA_OP8(STMT)                                                                                              \
     do {                                                                                                           \
         { int &x = x0; STMT; } { int &x = x1; STMT; } { int &x = x2; STMT; } { int &x = x3; STMT; }                \
@@ -168,6 +169,32 @@ __global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int
             if (KIND == 8) QOA_OP8(asm volatile("mad.hi.s32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
             if (KIND == 9) QOA_OP8(asm volatile("add.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
             if (KIND == 10) QOA_OP8(asm volatile("{ .reg .pred p; setp.lt.s32 p, %0, %1; selp.s32 %0, %2, %0, p; }" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 12) QOA_OP8(asm volatile("mad.lo.s32 %0, %0, 5, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 13) QOA_OP8(asm volatile("mul.lo.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 14) QOA_OP8(asm volatile("lop3.b32 %0, %0, %1, 0x55, 0x96;" : "+r"(x) : "r"(a)))
+            if (KIND == 15) QOA_OP8(asm volatile("shr.s32 %0, %0, 1;" : "+r"(x)))
+            if (KIND == 16) QOA_OP8(asm volatile("or.b32 %0, %0, 1;" : "+r"(x)))
+            if (KIND == 17) QOA_OP8(asm volatile("{ .reg .s32 t; add.s32 t, %0, %1; add.s32 %0, t, %2; }" : "+r"(x) : "r"(a), "r"(b)))
+            if (KIND == 18) {
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x4));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x5));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x6));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x7));
+            }
+            if (KIND == 19) { // 2 IMAD : 1 LOP3 : 1 one-register SHF
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x4));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("shr.s32 %0, %0, 1;" : "+r"(x6));
+                asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
+            }
             if (KIND == 11) {
                 long long y = x0;
                 asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x1), "r"(a));
@@ -216,7 +243,15 @@ cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
         case 8: launch_issue<8>(grid, block, d_out, iters); break;
         case 9: launch_issue<9>(grid, block, d_out, iters); break;
         case 10: launch_issue<10>(grid, block, d_out, iters); break;
-        default: launch_issue<11>(grid, block, d_out, iters); break;
+        case 11: launch_issue<11>(grid, block, d_out, iters); break;
+        case 12: launch_issue<12>(grid, block, d_out, iters); break;
+        case 13: launch_issue<13>(grid, block, d_out, iters); break;
+        case 14: launch_issue<14>(grid, block, d_out, iters); break;
+        case 15: launch_issue<15>(grid, block, d_out, iters); break;
+        case 16: launch_issue<16>(grid, block, d_out, iters); break;
+        case 17: launch_issue<17>(grid, block, d_out, iters); break;
+        case 18: launch_issue<18>(grid, block, d_out, iters); break;
+        default: launch_issue<19>(grid, block, d_out, iters); break;
         }
         cudaEventRecord(t1);
         e = cudaEventSynchronize(t1);
