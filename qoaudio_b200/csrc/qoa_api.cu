@@ -178,9 +178,31 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
     uint64_t max_bytes = 0;
     static const bool enabled = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0); // development aid
     const bool many = enabled && items.size() >= 32; // a handful of copies is cheaper through the copy engines
+    const cudaMemcpyKind kind = host_is_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    static const bool use_2d = !(getenv("QOA_B200_COPY_2D") && atoi(getenv("QOA_B200_COPY_2D")) == 0); // development aid
     for (size_t k = 0; k < items.size(); ++k) {
         const CopyItem &it = items[k];
         if (it.bytes == 0) continue;
+        // Equal-sized buffers at a constant pitch on both sides (a batch tensor of equal-length streams): the whole run is
+        // ONE strided copy on a copy engine -- full PCIe rate, and it overlaps the kernels of the neighbouring pipeline
+        // stages, which an SM copy kernel cannot while the encode kernel fills every SM.
+        if (use_2d && it.bytes >= (16u << 10) && k + 1 < items.size() && items[k + 1].bytes == it.bytes) {
+            const ptrdiff_t ps = static_cast<const char *>(items[k + 1].src) - static_cast<const char *>(it.src);
+            const ptrdiff_t pd = static_cast<char *>(items[k + 1].dst) - static_cast<char *>(it.dst);
+            const ptrdiff_t lim = 0x7fffffff; // cudaDeviceProp::memPitch
+            if (ps >= (ptrdiff_t)it.bytes && pd >= (ptrdiff_t)it.bytes && ps <= lim && pd <= lim) {
+                size_t r = k + 1;
+                while (r + 1 < items.size() && items[r + 1].bytes == it.bytes &&
+                       static_cast<const char *>(items[r + 1].src) - static_cast<const char *>(items[r].src) == ps &&
+                       static_cast<char *>(items[r + 1].dst) - static_cast<char *>(items[r].dst) == pd)
+                    ++r;
+                if (r - k + 1 >= 8) {
+                    CHECK_CUDA(ctx, cudaMemcpy2DAsync(it.dst, (size_t)pd, it.src, (size_t)ps, it.bytes, r - k + 1, kind, s));
+                    k = r;
+                    continue;
+                }
+            }
+        }
         const void *host = host_is_src ? it.src : it.dst;
         const bool aligned = ((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 15) == 0;
         // SM copies over PCIe reach ~22 GB/s against ~55 GB/s for the copy engines, a cudaMemcpyAsync call costs ~4 us:
@@ -189,7 +211,7 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
             fast.push_back(it);
             max_bytes = std::max(max_bytes, it.bytes);
         } else {
-            CHECK_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.bytes, host_is_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s));
+            CHECK_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.bytes, kind, s));
         }
     }
     if (!fast.empty()) {

@@ -127,13 +127,20 @@ class Engine:
         finally:
             plan.close()
 
-    def decode_all_batch(self, streams, caps, mode=N.DECODE_ALL):
+    def decode_all_batch(self, streams, caps, mode=N.DECODE_ALL, out=None):
         """One-call host path (qoa_b200_decode_all_batch): large batches are pipelined over chunks of streams so that
         H2D, decode and D2H overlap.  streams: list of np.uint8 arrays; caps: capacity (i16 values) per stream.
+        out (optional): C-contiguous int16 array of shape (len(streams), >= max(caps)) to decode into, one row per
+        stream -- rows of one array (on either side) move as a single strided copy instead of one copy per stream.
         Returns (info structured array, status np.int32 array, list of np.int16 arrays of length caps[i])."""
         n = len(streams)
         bufs = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
-        outs = [np.empty(int(c), dtype=np.int16) for c in caps]
+        if out is not None:
+            assert out.dtype == np.int16 and out.ndim == 2 and out.flags.c_contiguous and out.shape[0] == n
+            assert n == 0 or out.shape[1] >= max(int(c) for c in caps)
+            outs = [out[i, :int(c)] for i, c in enumerate(caps)]
+        else:
+            outs = [np.empty(int(c), dtype=np.int16) for c in caps]
         info = np.zeros(n, dtype=INFO_DTYPE)
         status = np.zeros(n, dtype=np.int32)
         k = _Keep()

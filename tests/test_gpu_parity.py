@@ -496,6 +496,26 @@ def test_decode_all_batch_pipelined(eng):
         assert np.array_equal(outs[i][:infos2[i]["samples"]], outs2[i])
 
 
+def test_batch_tensor_rows_move_as_strided_copies(eng):
+    """Equal-length streams held as rows of one array (input and output) travel as single strided copies
+    (cudaMemcpy2DAsync) instead of one copy per stream; results must not depend on how the bytes travelled."""
+    ch, rate, n, count = 2, 32000, 5120 * 2 + 1234, 24
+    pcm = np.stack([signals.synth_pcm(21, i, ch, n, "noise" if i % 5 == 2 else "music") for i in range(count)])
+    st, outs = eng.encode_all_batch(list(pcm), [(ch, rate, n)] * count)      # rows of `pcm`: strided H2D
+    assert st == [0] * count
+    size = ob.encoded_size(ch, n)
+    rows = np.zeros((count, (size + 15) // 16 * 16), dtype=np.uint8)
+    for i in range(count):
+        assert outs[i].tobytes() == ob.encode_all(pcm[i], ch, rate, n)[1], i
+        rows[i, :size] = outs[i]
+    dec = np.full((count, n * ch + 24), 77, dtype=np.int16)
+    info, status, views = eng.decode_all_batch([rows[i, :size] for i in range(count)], [n * ch] * count, out=dec)
+    assert not status.any() and (info["samples"] == n * ch).all()
+    for i in range(count):
+        assert np.array_equal(dec[i, :n * ch], ob.decode_all(rows[i, :size].tobytes())[1]), i
+    assert (dec[:, n * ch:] == 77).all()                                      # nothing written past a row's samples
+
+
 def test_encode_all_batch_pipelined(eng, N):
     """Host batches above 1 GB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
     the device between chunks; the bytes must equal the one-shot result (= the oracle), invalid streams included."""
