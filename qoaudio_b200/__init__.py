@@ -7,4 +7,5 @@ from .api import (MAX_SLICES_PER_CHANNEL_PER_FRAME, QOA_FRAME_LEN, QOA_HEADER_SI
                   QOA_MAX_CHANNELS, QOA_SLICE_LEN, QOA_SLICES_PER_FRAME, DecodedQoa, DecodeError, EncodeError,
                   FrameHeader, ProcessingMode, QoaDecoder, QoaDesc, QoaEncoder, QoaEncoderBatch, QoaItem, decode_all,
                   decode_all_batch, encode_all, encode_all_batch, open_and_decode_all)
+from . import wavio  # noqa: F401
 from .engine import DecodePlan, EncoderBatch, Engine, default_engine  # noqa: F401

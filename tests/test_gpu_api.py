@@ -1,6 +1,7 @@
 """The reference crate's own unit tests (src/lib.rs:991-1298) re-expressed against the crate-shaped Python API, plus
 the two fuzz targets as seeded randomised tests.  GPU only."""
 import io
+import os
 import math
 
 import numpy as np
@@ -196,3 +197,39 @@ def test_fuzz_encode_round_trip(q):
     for (pcm, desc), enc, dec, (ch, n) in zip(items, encs, decs, shapes):
         assert enc == ob.encode_all(pcm, ch, 44100, n)[1]
         assert (dec.num_channels, dec.sample_rate, len(dec.samples)) == (ch, 44100, n * ch)
+
+
+def test_example_tools_wav_to_qoa_and_back(q, tmp_path):
+    """examples/encode.py / decode.py (the reference's examples/encode.rs, decode.rs): single-file and batch forms."""
+    import subprocess
+    import sys as _sys
+    from conftest import ROOT
+    shapes = [(1, 8000, 777), (2, 44100, 5120 * 2 + 33), (6, 48000, 6000)]
+    wavs, pcms = [], []
+    for i, (ch, rate, n) in enumerate(shapes):
+        pcm = signals.synth_pcm(31, i, ch, n)
+        path = tmp_path / f"in{i}.wav"
+        q.wavio.write_wav(path, ch, rate, pcm)
+        wavs.append(str(path))
+        pcms.append(pcm)
+    (tmp_path / "bad.wav").write_bytes(b"RIFF" + bytes(20))
+    enc = [_sys.executable, os.path.join(ROOT, "examples", "encode.py")]
+    dec = [_sys.executable, os.path.join(ROOT, "examples", "decode.py")]
+    r = subprocess.run(enc + ["--out-dir", str(tmp_path / "q")] + wavs + [str(tmp_path / "bad.wav"), str(tmp_path / "nope.wav")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "does not exist" in r.stderr and "cannot read" in r.stderr, r.stderr
+    qoas = []
+    for i, (ch, rate, n) in enumerate(shapes):
+        data = (tmp_path / "q" / f"in{i}.qoa").read_bytes()
+        assert data == ob.encode_all(pcms[i], ch, rate, n)[1]
+        qoas.append(str(tmp_path / "q" / f"in{i}.qoa"))
+    r = subprocess.run(dec + ["--out-dir", str(tmp_path / "w")] + qoas, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for i, (ch, rate, n) in enumerate(shapes):
+        got = q.wavio.read_wav(tmp_path / "w" / f"in{i}.wav")
+        assert got[:3] == (ch, rate, 16)
+        assert np.array_equal(got[3], ob.decode_all((tmp_path / "q" / f"in{i}.qoa").read_bytes())[1])
+    r = subprocess.run(enc + [wavs[1], str(tmp_path / "one.qoa")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and (tmp_path / "one.qoa").read_bytes() == (tmp_path / "q" / "in1.qoa").read_bytes()
+    r = subprocess.run(dec + [str(tmp_path / "one.qoa"), str(tmp_path / "one.wav")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and (tmp_path / "one.wav").read_bytes() == (tmp_path / "w" / "in1.wav").read_bytes()
