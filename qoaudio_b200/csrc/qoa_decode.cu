@@ -811,7 +811,10 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
     const uint32_t fpw = 32 / P;               // frames per warp
     const uint32_t S = (ch & 1) ? 2u : 1u;     // slices per tile row
     const uint32_t row_bytes = S * kSliceLen * ch * 2;
-    const uint32_t pitch = row_bytes + 16;     // pad: neighbouring rows start in different bank groups
+    // Row pitch = an odd multiple of 16 bytes: rows start 4 (mod 8) banks apart, so the per-sample staging stores of a
+    // warp (one 32-bit word per lane, lanes = frames x pairs) hit each bank at most twice.  An even multiple lines
+    // every frame's word up on the same banks (6 channels: 240 + 16 = 256 bytes was a 10-way conflict).
+    const uint32_t pitch = row_bytes + (((row_bytes >> 4) & 1) ? 0 : 16);
     const uint32_t fl = lane / P, p = lane - fl * P; // frame within the warp, pair within the frame
     const uint64_t fi = ((uint64_t)blockIdx.x * kWarps + warp) * fpw + fl;
 
