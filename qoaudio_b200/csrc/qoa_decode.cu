@@ -451,17 +451,39 @@ struct PairLoop<20> {
     static __device__ __forceinline__ void run(Chain &, Chain &, uint32_t, uint32_t, uint2, uint2, uint32_t *) {}
 };
 
+// Two consecutive samples of ONE channel -> the output word (r1 << 16) | (r0 & 0xffff).  The second sample is clamped
+// by the same I2IP that builds the word (its other operand, r0, is already in range), so the pair costs one
+// instruction less than two clamps plus a pack.
+template <int I>
+__device__ __forceinline__ uint32_t decode_two_steps(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
+{
+    const int r0 = decode_step<I>(c, row, hi, lo);
+    const int2 t = lds_v2(row | code_off<I + 1>(hi, lo));
+    const int x1 = ((c.w0 * c.h0 + c.w1 * c.h1 + c.w2 * c.h2 + c.w3 * c.h3) >> 13) + t.x;
+    uint32_t packed;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(x1), "r"(r0));
+    const int r1 = (int)packed >> 16;
+    c.w0 += c.s0 * t.y;
+    c.w1 += c.s1 * t.y;
+    c.w2 += c.s2 * t.y;
+    c.w3 += c.s3 * t.y;
+    c.h0 = c.h1; c.h1 = c.h2; c.h2 = c.h3; c.h3 = r1;
+    c.s0 = c.s1; c.s1 = c.s2; c.s2 = c.s3; c.s3 = sign_pm1(r1);
+    return packed;
+}
+
 template <int I>
 struct SingleLoop {
-    static __device__ __forceinline__ void run(Chain &a, uint32_t row_a, uint2 wa, int16_t *o)
+    // Decodes samples I..19 of a slice for one channel, two per step; o[i / 2] = samples (i, i + 1) as one word.
+    static __device__ __forceinline__ void run(Chain &a, uint32_t row_a, uint2 wa, uint32_t *o)
     {
-        o[I] = (int16_t)decode_step<I>(a, row_a, wa.x, wa.y);
-        SingleLoop<I + 1>::run(a, row_a, wa, o);
+        o[I / 2] = decode_two_steps<I>(a, row_a, wa.x, wa.y);
+        SingleLoop<I + 2>::run(a, row_a, wa, o);
     }
 };
 template <>
 struct SingleLoop<20> {
-    static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, int16_t *) {}
+    static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, uint32_t *) {}
 };
 
 // ---- fast path for uniform mono / stereo batches ---------------------------------------------------------------
@@ -680,12 +702,10 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
                 const uint2 ra = lds64(in_ring + ((byte >> 4) & 3) * 512 + (byte & 8));
                 const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
                 const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
-                int16_t r[20];
-                SingleLoop<0>::run(a, row_a, wa, r);
+                uint32_t o[10];
+                SingleLoop<0>::run(a, row_a, wa, o);
 #pragma unroll
-                for (int i = 0; i < 5; ++i) // 40 bytes per slice: rows stay 8-byte aligned
-                    sts64(dst_s + i * 8, __byte_perm((uint32_t)(uint16_t)r[4 * i], (uint32_t)(uint16_t)r[4 * i + 1], 0x5410),
-                          __byte_perm((uint32_t)(uint16_t)r[4 * i + 2], (uint32_t)(uint16_t)r[4 * i + 3], 0x5410));
+                for (int i = 0; i < 5; ++i) sts64(dst_s + i * 8, o[2 * i], o[2 * i + 1]); // 40 bytes per slice: rows stay 8-byte aligned
             }
         }
         ++in_row;
@@ -965,13 +985,13 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     for (uint32_t k = 0; k < ngroups; ++k) {
         const uint2 wa = ldg_be64(sp + (uint64_t)k * ch * 8);
         const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
-        int16_t o[20];
+        uint32_t o[10];
         SingleLoop<0>::run(a, row_a, wa, o);
         const uint32_t base = k * kSliceLen;
         const uint32_t emit = min((uint32_t)kSliceLen, nsamp - base); // :320-328
 #pragma unroll
         for (int i = 0; i < 20; ++i)
-            if ((uint32_t)i < emit) op[(uint64_t)(base + i) * ch] = o[i];
+            if ((uint32_t)i < emit) op[(uint64_t)(base + i) * ch] = (int16_t)(o[i / 2] >> (16 * (i & 1)));
     }
 }
 
