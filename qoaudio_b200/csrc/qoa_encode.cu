@@ -28,6 +28,7 @@ constexpr int kEncWarps = kEncThreads / 32;
 constexpr int kChunkSlices = 16;                         // slices staged per refill
 constexpr int kChunkSamples = kChunkSlices * kSliceLen;  // 320 samples per chain
 constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kFastMaxWarps = 148 * 8;              // latency mode up to two warps per scheduler (measured crossover: see DESIGN.md)
 
 // Candidate LUT: entry (idx, sf), idx = clamp(scaled, -8, 8) + 8, at byte (idx * 16 + sf) * 16 holding
 // {dequantized, quantized, dequantized >> 4, 0}.  A quarter-warp (8 scalefactors) reads 8 distinct 16-byte bank groups
@@ -85,6 +86,110 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
     return v;
 }
 
+// ---- latency mode (few chains: every warp is alone on its scheduler and the step is a dependency chain) -------------
+// For a fixed scalefactor the map residual -> (quantized code, dequantized value) of :567-572 (qoa_div, clamp, two
+// table lookups) is a monotone step function of the residual with seven thresholds, as long as the 32-bit product in
+// qoa_div does not wrap (|v| < 32768 for scalefactor 0, < 229356 for scalefactor 1, never for the others given
+// |v| <= 32768 + 2^18).  Seven compares and a three-level select tree replace the multiply, the sign fix-up, the clamp
+// and the ~30-cycle shared-memory lookup on the critical path.  The predictor is re-associated so that only three
+// instructions sit between the previous sample and the residual: with negated weights nw = -w and
+// K = 8192 * s + 8191,   s - ((sum w*h) >> 13) == (K + sum nw*h) >> 13   (exact while K + sum nw*h fits 32 bits),
+// and the weight update of the previous step is applied lazily:  sum_{i<3} nw_i' * h_i = D + delta * NB  with D and NB
+// built from values known one step earlier.  A step that leaves the exact domain (|v| >= lim, which also catches the
+// 32-bit overflow of K + sum nw*h: the wrapped residual is then >= 229376 in magnitude) sets a sticky flag and the
+// whole slice is redone with candidate_step(); on music that is ~1 % of the slices, on full-scale noise about half.
+// The table is built ON THE DEVICE from the very expressions candidate_step() uses (fast_table_kernel).
+struct FastTab {
+    int b[7]; // ascending thresholds: the code changes at v == b[k]
+    int x[8]; // (dequantized << 3) | quantized for v < b[0], b[0] <= v < b[1], ..., v >= b[6]
+    int lim;  // exact for -lim <= v < lim
+};
+__device__ FastTab g_fast_tab[16];
+__device__ int g_fast_ok;
+
+__global__ void fast_table_kernel()
+{
+    const int sf = threadIdx.x;
+    const int recip = c_recip[sf];
+    const int lim = sf == 0 ? 32768 : 196608;
+    FastTab t;
+    int nb = 0, prev = -1;
+    bool ok = true;
+    for (int v = -lim; v < lim; ++v) {
+        const int n = (int)((uint32_t)v * (uint32_t)recip + 32768u) >> 16;
+        const int f = n + max(-1, min(1, v)) - max(-1, min(1, n));
+        const int q = c_quant[max(-8, min(8, f)) + 8];
+        if (q != prev) {
+            if (prev >= 0) {
+                if (nb < 7) t.b[nb] = v;
+                ++nb;
+            }
+            if (nb < 8) t.x[nb] = c_dequant[sf * 8 + q] * 8 + q;
+            prev = q;
+        }
+    }
+    ok = nb == 7;
+    if (ok)
+        for (int k = 0; k < 8; ++k) ok = ok && (t.x[k] & 7) == (k < 4 ? 7 - 2 * k : 2 * (k - 4)); // codes 7,5,3,1,0,2,4,6
+    t.lim = lim;
+    g_fast_tab[sf] = t;
+    if (!ok) atomicExch(&g_fast_ok, 0);
+}
+
+__device__ __forceinline__ int keep(int x)
+{
+    asm("mov.b32 %0, %0;" : "+r"(x));
+    return x;
+}
+
+struct FCand {
+    int a, b, c, d;         // history, d newest
+    int nw0, nw1, nw2, nw3; // negated weights as of one step ago (the update by dp is pending)
+    int nsx, nsa, nsb, nsc; // negated +/-1 signs of the history of one step ago: the pending update's signs
+    int ga, gb, gc;         // nsx * a, nsa * b, nsb * c
+    int dp;                 // pending delta (dequantized >> 4 of the previous step)
+};
+
+__device__ __forceinline__ void fast_step(FCand &l, const FastTab &t, int s, long long &err, uint32_t &pen, uint32_t &codes,
+                                          uint32_t &trip)
+{
+    // keep() pins the association: the compiler would otherwise re-chain the whole sum behind the newest sample
+    const int K = s * 8192 + 8191;
+    const int D = keep(l.nw0 * l.a + l.nw1 * l.b + l.nw2 * l.c + K);
+    const int NB = keep(l.ga + l.gb + l.gc);
+    const int E = keep(l.dp * NB + D);
+    const int nw3 = keep(l.nsc * l.dp + l.nw3);
+    const int v = (nw3 * l.d + E) >> 13; // == s - predict
+    l.nw0 += l.nsx * l.dp;               // the pending update :821-828
+    l.nw1 += l.nsa * l.dp;
+    l.nw2 += l.nsb * l.dp;
+    l.nw3 = nw3;
+    const int ws = (l.nw0 * l.nw0 + l.nw1 * l.nw1 + l.nw2 * l.nw2 + l.nw3 * l.nw3) >> 18; // :814-817
+    const int penalty = __viaddmax_s32(ws, -0x8ff, 0);
+    const int x01 = v >= t.b[0] ? t.x[1] : t.x[0];
+    const int x23 = v >= t.b[2] ? t.x[3] : t.x[2];
+    const int x45 = v >= t.b[4] ? t.x[5] : t.x[4];
+    const int x67 = v >= t.b[6] ? t.x[7] : t.x[6];
+    const int xl = v >= t.b[1] ? x23 : x01;
+    const int xh = v >= t.b[5] ? x67 : x45;
+    const int x = v >= t.b[3] ? xh : xl;
+    trip |= (uint32_t)(v + t.lim) >= 2u * (uint32_t)t.lim;
+    const int dq = x >> 3;
+    const int p = s - v;
+    const int r = max(__viaddmin_s32(p, dq, 32767), -32768); // :573
+    const int e = s - r;                                     // :575
+    err += (long long)e * (long long)e;                      // :576
+    pen += (uint32_t)penalty * (uint32_t)penalty;
+    codes = codes * 8u + (uint32_t)(x & 7); // :584
+    const int nsd = (l.d >> 31) * -2 - 1; // -sign: one shift + one IMAD
+    l.ga = l.gb;
+    l.gb = l.gc;
+    l.gc = l.nsc * l.d;
+    l.nsx = l.nsa; l.nsa = l.nsb; l.nsb = l.nsc; l.nsc = nsd;
+    l.a = l.b; l.b = l.c; l.c = l.d; l.d = r;
+    l.dp = x >> 7; // dequantized >> 4
+}
+
 // Lexicographic (total, first, sf) arg-min over a half-warp; only used when two candidates tie on the total rank.
 __device__ __noinline__ uint32_t winner_slow(uint64_t total, uint64_t first, uint32_t sf)
 {
@@ -105,7 +210,8 @@ __device__ __noinline__ uint32_t winner_slow(uint64_t total, uint64_t first, uin
 
 // One warp = two chains (half-warps).  Both halves run the same number of iterations (the longer chain's slice count);
 // a half whose chain is exhausted computes on zeros and commits nothing, so every shuffle is warp-converged.
-__global__ void __launch_bounds__(kEncThreads, 7)
+template <bool FAST>
+__global__ void __launch_bounds__(kEncThreads, FAST ? 1 : 7)
 encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const EncJob *__restrict__ jobs,
               const EncChain *__restrict__ chains, uint32_t n_chains, int32_t *__restrict__ lms_state, int zero)
 {
@@ -128,6 +234,8 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
     const uint32_t lut_lane = smem_u32(&sm.lut[0]) + sf * 16 + 8 * 256;
     const uint32_t stage = smem_u32(&sm.stage[warp_in_cta][half][0]);
     const int recip = c_recip[sf];
+    FastTab ft;
+    if (FAST) ft = g_fast_tab[sf];
 
     EncJob job;
     job.pcm_off = 0; job.out_off = 0; job.channels = 1; job.rate = 0; job.nsamples = 0; job.lms_base = 0;
@@ -202,7 +310,38 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
         uint32_t pen = 0, first_err = 0, first_pen = 0;
         uint32_t codes_a = 0, codes_b = 0; // samples 0..9 and 10..19, 3 bits each
         const uint32_t sp = stage + (j & (kChunkSlices - 1)) * (kSliceLen * 2);
-        if (__all_sync(kFull, len == kSliceLen || !active)) { // steady state (an idle half computes on zeros)
+        bool done = false;
+        if (FAST && __all_sync(kFull, len == kSliceLen || !active)) { // latency mode: threshold search, lazy update
+            FCand fl;
+            fl.a = cur.h0; fl.b = cur.h1; fl.c = cur.h2; fl.d = cur.h3;
+            fl.nw0 = -cur.w0; fl.nw1 = -cur.w1; fl.nw2 = -cur.w2; fl.nw3 = -cur.w3;
+            fl.nsx = 0; fl.nsa = -cur.s0; fl.nsb = -cur.s1; fl.nsc = -cur.s2;
+            fl.ga = 0; fl.gb = fl.nsa * fl.b; fl.gc = fl.nsb * fl.c;
+            fl.dp = 0;
+            uint32_t trip = 0;
+            fast_step(fl, ft, lds_s16(sp), err, pen, codes_a, trip);
+            first_err = (uint32_t)err;
+            first_pen = pen;
+#pragma unroll
+            for (int i = 1; i < 10; ++i) fast_step(fl, ft, lds_s16(sp + i * 2), err, pen, codes_a, trip);
+#pragma unroll
+            for (int i = 10; i < 20; ++i) fast_step(fl, ft, lds_s16(sp + i * 2), err, pen, codes_b, trip);
+            if (!__any_sync(kFull, trip != 0)) {
+                done = true;
+                l.h0 = fl.a; l.h1 = fl.b; l.h2 = fl.c; l.h3 = fl.d;
+                l.w0 = -(fl.nw0 + fl.nsx * fl.dp); // the last pending update
+                l.w1 = -(fl.nw1 + fl.nsa * fl.dp);
+                l.w2 = -(fl.nw2 + fl.nsb * fl.dp);
+                l.w3 = -(fl.nw3 + fl.nsc * fl.dp);
+                l.s0 = -fl.nsa; l.s1 = -fl.nsb; l.s2 = -fl.nsc; l.s3 = sign_pm1(fl.d);
+            } else { // some candidate left the exact domain: redo the slice with the reference arithmetic
+                err = 0;
+                pen = 0;
+                codes_a = codes_b = 0;
+            }
+        }
+        if (done) {
+        } else if (__all_sync(kFull, len == kSliceLen || !active)) { // steady state (an idle half computes on zeros)
             candidate_step(l, lds_s16(sp), recip, lut_lane, err, pen, codes_a, zero);
             first_err = (uint32_t)err; // error^2 of one sample fits 32 bits
             first_pen = pen;
@@ -231,19 +370,30 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
         // ---- winner within the half-warp: min total rank; ties (rare) resolved by (first-sample rank, sf)
         const uint64_t total = (uint64_t)err + pen;
         uint32_t hi = (uint32_t)(total >> 32), lo = (uint32_t)total;
+        // per-half minimum.  Latency mode: one warp-wide REDUX per half (the other half contributes the neutral
+        // element) instead of four dependent shuffle + min stages; in the throughput kernel the butterfly is faster.
+        auto half_min = [&](uint32_t x) {
+            if (FAST) {
+                const uint32_t m0 = __reduce_min_sync(kFull, half ? 0xffffffffu : x);
+                const uint32_t m1 = __reduce_min_sync(kFull, half ? x : 0xffffffffu);
+                return half ? m1 : m0;
+            }
+#pragma unroll
+            for (int m = 8; m >= 1; m >>= 1) x = min(x, __shfl_xor_sync(kFull, x, m));
+            return x;
+        };
         uint32_t mh = hi;
         if (__any_sync(kFull, hi != 0)) {
-#pragma unroll
-            for (int m = 8; m >= 1; m >>= 1) mh = min(mh, __shfl_xor_sync(kFull, mh, m));
+            mh = half_min(hi);
             if (hi != mh) lo = 0xffffffffu; // out of the race (a true 0xffffffff with hi == mh still ties correctly below)
         }
-        uint32_t ml = lo;
-#pragma unroll
-        for (int m = 8; m >= 1; m >>= 1) ml = min(ml, __shfl_xor_sync(kFull, ml, m));
+        const uint32_t ml = half_min(lo);
         const bool is_min = hi == mh && (uint32_t)total == ml;
-        const uint32_t votes = (__ballot_sync(kFull, is_min) >> (half * 16)) & 0xffffu;
+        const uint32_t ballot = __ballot_sync(kFull, is_min);
+        const uint32_t votes = (ballot >> (half * 16)) & 0xffffu;
         uint32_t win = __ffs(votes) - 1;
-        if (__any_sync(kFull, (votes & (votes - 1)) != 0)) // some half has a tie on the total rank
+        const uint32_t b0 = ballot & 0xffffu, b1 = ballot >> 16; // every lane sees both halves: no second vote needed
+        if ((b0 & (b0 - 1)) | (b1 & (b1 - 1))) // some half has a tie on the total rank (warp-uniform)
             win = winner_slow(total, (uint64_t)first_err + first_pen, sf);
         const int src_lane = (int)((lane & 16) | win);
         const int nh0 = __shfl_sync(kFull, l.h0, src_lane), nh1 = __shfl_sync(kFull, l.h1, src_lane);
@@ -270,13 +420,49 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
     }
 }
 
+static cudaError_t ensure_fast_table()
+{
+    static bool ready[64] = {false}, usable[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!ready[dev]) {
+        const int one = 1;
+        int ok = 0;
+        if ((e = cudaMemcpyToSymbol(g_fast_ok, &one, sizeof one)) != cudaSuccess) return e;
+        fast_table_kernel<<<1, 16>>>();
+        if ((e = cudaMemcpyFromSymbol(&ok, g_fast_ok, sizeof ok)) != cudaSuccess) return e;
+        usable[dev] = ok != 0;
+        ready[dev] = true;
+    }
+    return usable[dev] ? cudaSuccess : cudaErrorNotSupported;
+}
+
 cudaError_t launch_encode(const int16_t *d_pcm, uint8_t *d_out, const EncJob *d_jobs, const EncChain *d_chains,
                           uint32_t n_chains, int32_t *d_lms, cudaStream_t s, int *n_launches)
 {
     if (n_chains == 0) return cudaSuccess;
     const uint32_t warps = (n_chains + 1) / 2;
-    const uint32_t blocks = (warps + kEncWarps - 1) / kEncWarps;
-    encode_kernel<<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms, 0);
+    // Few chains: the step is a pure dependency chain (one warp per scheduler or less) -> the latency-mode kernel,
+    // one warp per CTA so that the warps spread over the SMs.  QOA_B200_ENC_FAST = 0 / 1 forces the choice
+    // (development aid).
+    static const int forced = getenv("QOA_B200_ENC_FAST") ? atoi(getenv("QOA_B200_ENC_FAST")) : -1;
+    bool fast = forced >= 0 ? forced != 0 : warps <= kFastMaxWarps;
+    if (fast) {
+        const cudaError_t e = ensure_fast_table();
+        if (e == cudaErrorNotSupported)
+            fast = false; // the table did not validate: keep the exact kernel
+        else if (e != cudaSuccess)
+            return e;
+    }
+    if (fast) {
+        const uint32_t blocks = (warps + kEncWarps - 1) / kEncWarps;
+        encode_kernel<true><<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms, 0);
+    } else {
+        const uint32_t blocks = (warps + kEncWarps - 1) / kEncWarps;
+        encode_kernel<false><<<blocks, kEncThreads, 0, s>>>(d_pcm, d_out, d_jobs, d_chains, n_chains, d_lms, 0);
+    }
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
