@@ -1,6 +1,7 @@
 """GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
 and the committed golden vectors.  Bit-exact: identical .qoa bytes on encode, identical i16 samples on decode."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -514,6 +515,39 @@ def test_batch_tensor_rows_move_as_strided_copies(eng):
     for i in range(count):
         assert np.array_equal(dec[i, :n * ch], ob.decode_all(rows[i, :size].tobytes())[1]), i
     assert (dec[:, n * ch:] == 77).all()                                      # nothing written past a row's samples
+
+
+@pytest.mark.parametrize("fast", ["0", "1"])
+def test_encode_kernel_variants(fast):
+    """Small batches take the latency-mode kernel (threshold search, lazily applied LMS update, exact redo of slices
+    that leave its domain), large ones the throughput kernel.  Both are forced in turn here (QOA_B200_ENC_FAST is read
+    once per process, hence the subprocess) on signals that do and do not trip the redo path."""
+    import subprocess
+    import sys
+    code = """
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests')
+import numpy as np, signals, qoaudio_b200
+from oracle import binding as ob
+eng = qoaudio_b200.default_engine()
+pcm, descs = [], []
+for i, (ch, n, kind) in enumerate([(2, 5120 * 3 + 777, 'music'), (1, 20000, 'noise'), (2, 30000, 'noise'), (6, 7001, 'music'),
+                                   (1, 5120, 'music'), (3, 19, 'noise')]):
+    pcm.append(signals.synth_pcm(41, i, ch, n, kind)); descs.append((ch, 44100, n))
+for name, sig in signals.edge_signals().items():
+    pcm.append(sig); descs.append((1, 8000, sig.size))
+loud = np.tile(np.array([32767, -32768, 32767, 32767, -32768, -32768], dtype=np.int16), 4000)  # worst-case residuals
+pcm.append(loud); descs.append((2, 48000, loud.size // 2))
+st, outs = eng.encode_all_batch(pcm, descs)
+assert st == [0] * len(descs)
+for p, d, o in zip(pcm, descs, outs):
+    assert o.tobytes() == ob.encode_all(p, *d)[1], d
+print('variants ok')
+"""
+    from conftest import ROOT
+    env = dict(os.environ, QOA_B200_ENC_FAST=fast)
+    r = subprocess.run([sys.executable, "-c", code.format(root=ROOT)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_encode_all_batch_pipelined(eng, N):
