@@ -19,6 +19,8 @@
 // fused VIADDMNMX; the squared error accumulates through one IMAD.WIDE; the 3-bit codes accumulate in two 30-bit
 // halves; PCM samples are staged de-interleaved in shared memory 16 slices at a time so the per-step fetch is one
 // broadcast LDS with an immediate offset.
+#include <mutex>
+
 #include "qoa_kernels.h"
 
 namespace qoa {
@@ -423,6 +425,8 @@ encode_kernel(const int16_t *__restrict__ pcm, uint8_t *__restrict__ out, const 
 static cudaError_t ensure_fast_table()
 {
     static bool ready[64] = {false}, usable[64] = {false};
+    static std::mutex mu; // contexts on different host threads may get here at the same time
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
