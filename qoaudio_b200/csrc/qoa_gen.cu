@@ -195,6 +195,24 @@ __global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int
                 asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
             }
+            if (KIND == 20 || KIND == 21) { // decode-like mixes over 17 instructions: 20 = 5 IMAD : 4 FFMA : 8 LOP3, 21 = 9 IMAD : 8 LOP3
+                float f0 = __int_as_float(x0), f1 = __int_as_float(x1), f2 = __int_as_float(x2), f3 = __int_as_float(x3);
+                const float fa = __int_as_float(a), fb = __int_as_float(b);
+#define QOA_I(x) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b))
+#define QOA_L(x) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b))
+#define QOA_F(x) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(fa), "f"(fb))
+                if (KIND == 20) {
+                    QOA_I(x4); QOA_L(x5); QOA_F(f0); QOA_L(x6); QOA_I(x7); QOA_L(x5); QOA_F(f1); QOA_L(x6); QOA_I(x4);
+                    QOA_L(x5); QOA_F(f2); QOA_L(x6); QOA_I(x7); QOA_L(x5); QOA_F(f3); QOA_L(x6); QOA_I(x4);
+                } else {
+                    QOA_I(x4); QOA_L(x5); QOA_I(x0); QOA_L(x6); QOA_I(x7); QOA_L(x5); QOA_I(x1); QOA_L(x6); QOA_I(x4);
+                    QOA_L(x5); QOA_I(x2); QOA_L(x6); QOA_I(x7); QOA_L(x5); QOA_I(x3); QOA_L(x6); QOA_I(x4);
+                }
+#undef QOA_I
+#undef QOA_L
+#undef QOA_F
+                if (KIND == 20) { x0 = __float_as_int(f0); x1 = __float_as_int(f1); x2 = __float_as_int(f2); x3 = __float_as_int(f3); }
+            }
             if (KIND == 11) {
                 long long y = x0;
                 asm volatile("mad.wide.s32 %0, %1, %2, %0;" : "+l"(y) : "r"(x1), "r"(a));
@@ -251,7 +269,9 @@ cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
         case 16: launch_issue<16>(grid, block, d_out, iters); break;
         case 17: launch_issue<17>(grid, block, d_out, iters); break;
         case 18: launch_issue<18>(grid, block, d_out, iters); break;
-        default: launch_issue<19>(grid, block, d_out, iters); break;
+        case 19: launch_issue<19>(grid, block, d_out, iters); break;
+        case 20: launch_issue<20>(grid, block, d_out, iters); break;
+        default: launch_issue<21>(grid, block, d_out, iters); break;
         }
         cudaEventRecord(t1);
         e = cudaEventSynchronize(t1);
@@ -264,7 +284,7 @@ cudaError_t run_int_issue_peak(int kind, int sm_count, double *thread_ops_per_s)
     cudaEventDestroy(t1);
     cudaFree(d_out);
     if (e != cudaSuccess) return e;
-    const double ops = (double)grid * block * (double)iters * 64.0; // 8 unrolled x 8 chains per iteration
+    const double ops = (double)grid * block * (double)iters * (kind >= 20 ? 8.0 * 17.0 : 64.0); // 8 unrolled x 8 chains (or the 17-instruction mixes)
     *thread_ops_per_s = ops / (best_ms * 1e-3);
     return cudaGetLastError();
 }
