@@ -178,6 +178,12 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
     uint64_t max_bytes = 0;
     static const bool enabled = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0); // development aid
     const bool many = enabled && items.size() >= 32; // a handful of copies is cheaper through the copy engines
+    // development aids: QOA_B200_COPY_KERNEL_MAX_KB_{H2D,D2H} move the crossovers
+    static const uint64_t max_h2d =
+        (getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D") ? (uint64_t)atoi(getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D")) : 256ull) << 10;
+    static const uint64_t max_d2h =
+        (getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H") ? (uint64_t)atoi(getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H")) : 1024ull) << 10;
+    const uint64_t kernel_max = host_is_src ? max_h2d : max_d2h;
     const cudaMemcpyKind kind = host_is_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
     static const bool use_2d = !(getenv("QOA_B200_COPY_2D") && atoi(getenv("QOA_B200_COPY_2D")) == 0); // development aid
     for (size_t k = 0; k < items.size(); ++k) {
@@ -205,9 +211,10 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
         }
         const void *host = host_is_src ? it.src : it.dst;
         const bool aligned = ((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 15) == 0;
-        // SM copies over PCIe reach ~22 GB/s against ~55 GB/s for the copy engines, a cudaMemcpyAsync call costs ~4 us:
-        // the kernel wins below ~256 KB per buffer
-        if (many && aligned && it.bytes < (256u << 10) && (known ? (*known)[k] != 0 : device_accessible(host))) {
+        // SM copies over PCIe reach ~22 GB/s reading host memory and ~37 GB/s writing it, against ~55 GB/s for the copy
+        // engines; one cudaMemcpyAsync call costs 4-8 us of host time.  Measured crossovers (tools/e2e_small_streams.py,
+        // tools/e2e_encode_probe.py): the kernel wins below ~256 KB per buffer host->device, below ~1 MB device->host.
+        if (many && aligned && it.bytes < kernel_max && (known ? (*known)[k] != 0 : device_accessible(host))) {
             fast.push_back(it);
             max_bytes = std::max(max_bytes, it.bytes);
         } else {
