@@ -228,7 +228,7 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
             return QOA_B200_E_NOMEM;
         }
         CHECK_CUDA(ctx, cudaMemcpyAsync(d_items, fast.data(), fast.size() * sizeof(CopyItem), cudaMemcpyHostToDevice, s));
-        CHECK_CUDA(ctx, launch_copy_items(d_items, (uint32_t)fast.size(), max_bytes, s));
+        CHECK_CUDA(ctx, launch_copy_items(d_items, (uint32_t)fast.size(), max_bytes, !host_is_src, s));
         ctx->launches += 1;
     }
     return 0;

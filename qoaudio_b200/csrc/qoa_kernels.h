@@ -64,7 +64,7 @@ struct CopyItem {
     void *dst;
     uint64_t bytes;
 };
-cudaError_t launch_copy_items(const CopyItem *d_items, uint32_t n_items, uint64_t max_bytes, cudaStream_t s);
+cudaError_t launch_copy_items(const CopyItem *d_items, uint32_t n_items, uint64_t max_bytes, bool to_host, cudaStream_t s);
 
 // ---- generators / microbenchmarks ----------------------------------------------------------------------------
 cudaError_t launch_gen_pcm(int16_t *d_pcm, uint64_t n_streams, uint64_t first_stream, uint32_t channels,
