@@ -114,6 +114,16 @@ struct qoa_b200_ctx {
                 return;
             }
     }
+    // Stream of the synchronous host-buffer entry points: an internal non-blocking stream rather than the legacy NULL
+    // stream (cudaMemcpyBatchAsync refuses the latter); nullptr if it cannot be created.
+    cudaStream_t host_stream()
+    {
+        if (!pipe_streams[0] && cudaStreamCreateWithFlags(&pipe_streams[0], cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            pipe_streams[0] = nullptr;
+        }
+        return pipe_streams[0];
+    }
     // Scratch blocks are recycled without waiting: safe as long as work is enqueued on one stream at a time.
     void enter(cudaStream_t s)
     {
@@ -174,24 +184,37 @@ bool device_accessible(const void *p)
 int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &items, bool host_is_src, cudaStream_t s,
                const std::vector<char> *known = nullptr)
 {
-    std::vector<CopyItem> fast;
-    uint64_t max_bytes = 0;
-    static const bool enabled = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0); // development aid
-    const bool many = enabled && items.size() >= 32; // a handful of copies is cheaper through the copy engines
-    // development aids: QOA_B200_COPY_KERNEL_MAX_KB_{H2D,D2H} move the crossovers
-    static const uint64_t max_h2d =
-        (getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D") ? (uint64_t)atoi(getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D")) : 256ull) << 10;
-    static const uint64_t max_d2h =
-        (getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H") ? (uint64_t)atoi(getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H")) : 1024ull) << 10;
-    const uint64_t kernel_max = host_is_src ? max_h2d : max_d2h;
+    // Three mechanisms, chosen per buffer (crossovers measured with tools/e2e_small_streams.py and
+    // tools/e2e_encode_probe.py; the environment variables are development aids):
+    //  (1) runs of >= 8 equal-sized buffers at a constant pitch on both sides (rows of a batch tensor): ONE strided copy
+    //      on a copy engine -- full PCIe rate, no per-buffer cost, overlaps the neighbouring stages' kernels;
+    //  (2) small pinned buffers: one copy kernel through mapped pinned memory (SM loads read host memory at ~22 GB/s;
+    //      device -> host goes through the bulk-copy engine at 35-42 GB/s), no per-buffer cost at all;
+    //  (3) the rest in ONE cudaMemcpyBatchAsync (CUDA 12.8+; ~0.9 us per buffer inside the driver, 45-49 GB/s for
+    //      128-512 KB buffers, on the copy engines) -- or, on the legacy NULL stream / an older driver, one
+    //      cudaMemcpyAsync per buffer (4-8 us of host time each).
+    static const bool kernel_on = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0);
+    static const bool use_2d = !(getenv("QOA_B200_COPY_2D") && atoi(getenv("QOA_B200_COPY_2D")) == 0);
+    static bool use_batch = !(getenv("QOA_B200_COPY_BATCH") && atoi(getenv("QOA_B200_COPY_BATCH")) == 0);
+    static const long env_h2d = getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D") ? atol(getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D")) : -1;
+    static const long env_d2h = getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H") ? atol(getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H")) : -1;
+#if CUDART_VERSION >= 12080
+    const bool batch_ok = use_batch && s != nullptr && s != cudaStreamLegacy;
+#else
+    const bool batch_ok = false;
+#endif
+    // kernel-vs-copy-engine crossover: against the batched call 32 KB (host -> device) / 96 KB (device -> host),
+    // against one call per buffer 256 KB / 1 MB
+    const long env_max = host_is_src ? env_h2d : env_d2h;
+    const uint64_t kernel_max =
+        (env_max >= 0 ? (uint64_t)env_max : batch_ok ? (host_is_src ? 32ull : 96ull) : (host_is_src ? 256ull : 1024ull)) << 10;
+    const bool many = kernel_on && items.size() >= 32; // a handful of copies is cheaper through the copy engines
     const cudaMemcpyKind kind = host_is_src ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-    static const bool use_2d = !(getenv("QOA_B200_COPY_2D") && atoi(getenv("QOA_B200_COPY_2D")) == 0); // development aid
+    std::vector<CopyItem> fast, rest;
+    uint64_t max_bytes = 0;
     for (size_t k = 0; k < items.size(); ++k) {
         const CopyItem &it = items[k];
         if (it.bytes == 0) continue;
-        // Equal-sized buffers at a constant pitch on both sides (a batch tensor of equal-length streams): the whole run is
-        // ONE strided copy on a copy engine -- full PCIe rate, and it overlaps the kernels of the neighbouring pipeline
-        // stages, which an SM copy kernel cannot while the encode kernel fills every SM.
         if (use_2d && it.bytes >= (16u << 10) && k + 1 < items.size() && items[k + 1].bytes == it.bytes) {
             const ptrdiff_t ps = static_cast<const char *>(items[k + 1].src) - static_cast<const char *>(it.src);
             const ptrdiff_t pd = static_cast<char *>(items[k + 1].dst) - static_cast<char *>(it.dst);
@@ -211,14 +234,11 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
         }
         const void *host = host_is_src ? it.src : it.dst;
         const bool aligned = ((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 15) == 0;
-        // SM copies over PCIe reach ~22 GB/s reading host memory and ~37 GB/s writing it, against ~55 GB/s for the copy
-        // engines; one cudaMemcpyAsync call costs 4-8 us of host time.  Measured crossovers (tools/e2e_small_streams.py,
-        // tools/e2e_encode_probe.py): the kernel wins below ~256 KB per buffer host->device, below ~1 MB device->host.
         if (many && aligned && it.bytes < kernel_max && (known ? (*known)[k] != 0 : device_accessible(host))) {
             fast.push_back(it);
             max_bytes = std::max(max_bytes, it.bytes);
         } else {
-            CHECK_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.bytes, kind, s));
+            rest.push_back(it);
         }
     }
     if (!fast.empty()) {
@@ -231,6 +251,27 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
         CHECK_CUDA(ctx, launch_copy_items(d_items, (uint32_t)fast.size(), max_bytes, !host_is_src, s));
         ctx->launches += 1;
     }
+#if CUDART_VERSION >= 12080
+    if (batch_ok && rest.size() >= 2) {
+        std::vector<void *> dsts(rest.size()), srcs(rest.size());
+        std::vector<size_t> sizes(rest.size());
+        for (size_t k = 0; k < rest.size(); ++k) {
+            dsts[k] = rest[k].dst;
+            srcs[k] = const_cast<void *>(rest[k].src);
+            sizes[k] = rest[k].bytes;
+        }
+        cudaMemcpyAttributes attr;
+        memset(&attr, 0, sizeof attr);
+        attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        attr.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+        size_t first = 0, fail = 0;
+        if (cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), rest.size(), &attr, &first, 1, &fail, s) == cudaSuccess)
+            return 0;
+        cudaGetLastError();
+        use_batch = false; // e.g. an older driver: one call per buffer, now and on every later call
+    }
+#endif
+    for (const CopyItem &it : rest) CHECK_CUDA(ctx, cudaMemcpyAsync(it.dst, it.src, it.bytes, kind, s));
     return 0;
 }
 
@@ -429,7 +470,7 @@ extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc 
         if (total >= (512ull << 20) && per_frame_step && (256ull << 20) / per_frame_step >= 2)
             return encode_all_batch_pipelined(ctx, descs, pcm, pcm_len, out, out_cap, out_len, status, n, total);
     }
-    cudaStream_t s = nullptr;
+    cudaStream_t s = ctx->host_stream();
     // lay the valid streams out in two device arenas
     std::vector<uint64_t> pcm_off(n, 0), out_off(n, 0);
     std::vector<size_t> caps(n, 0);
@@ -582,7 +623,7 @@ static int encode_host(qoa_b200_encoder_batch *enc, const int16_t *const *pcm, c
         return QOA_B200_E_ARG;
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = nullptr;
+    cudaStream_t s = enc->ctx->host_stream();
     const size_t n = enc->descs.size();
     std::vector<uint64_t> pcm_off(n, 0), out_off(n, 0);
     std::vector<uint32_t> chunk(n, 0);
@@ -996,7 +1037,8 @@ static int plan_create_host(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const 
 extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
                                            int mode, qoa_b200_decode_plan **out)
 {
-    return plan_create_host(ctx, qoa, len, n, mode, nullptr, out);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) cudaGetLastError(); // reported by plan_create_host
+    return plan_create_host(ctx, qoa, len, n, mode, ctx->host_stream(), out);
 }
 
 extern "C" void qoa_b200_decode_plan_destroy(qoa_b200_decode_plan *plan)
