@@ -396,7 +396,7 @@ def main():
             dt = reduce_max(time.perf_counter() - t0)
             encode["e2e"] = {"value": ES * per * world * reps / dt / 1e6, "unit": "Msamples/s",
                              "h2d_bytes_per_step": ES * per * 2, "d2h_bytes_per_step": ES * osz, "ms_per_step": dt / reps * 1e3,
-                             "api": "qoa_b200_encode_all_batch (pinned host buffers, 24 frames per stream per call: four time chunks)"}
+                             "api": "qoa_b200_encode_all_batch (pinned host buffers, 24 frames per stream per call, pipelined in time chunks of ~176 MB of PCM)"}
             del h_pcm, h_enc
         del epcm, eout
 

@@ -447,6 +447,13 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
                                       const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
                                       size_t *out_len, int32_t *status, size_t n, uint64_t total_pcm_values);
 
+// PCM values (i16) per time chunk of the pipelined host encode path; QOA_B200_ENC_CHUNK_MB (MB of PCM) is a development aid.
+static uint64_t enc_chunk_values()
+{
+    static const uint64_t v = (getenv("QOA_B200_ENC_CHUNK_MB") ? (uint64_t)atoi(getenv("QOA_B200_ENC_CHUNK_MB")) : 176ull) << 19;
+    return std::max<uint64_t>(v, 1);
+}
+
 extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
                                          const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap,
                                          size_t *out_len, int32_t *status, size_t n)
@@ -459,15 +466,15 @@ extern "C" int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc 
     }
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     {
-        // >= 1 GB of PCM: overlap the copies with the kernel in time chunks of ~512 MB (at least two frames of every
-        // stream per chunk so that per-chunk table uploads and launches stay small next to the chunk's kernel;
-        // per-stream copies are batched into one kernel when the host buffers are pinned).
+        // >= 3 chunks of PCM: overlap the copies with the kernel in time chunks of ~176 MB (measured on the C4 shape:
+        // 512 MB chunks 47.6 ms, 256 MB 42.7 ms, 84-170 MB 41.4 ms for 2 GB of PCM; a chunk holds whole frames of every
+        // stream, at least one).
         uint64_t total = 0, per_frame_step = 0;
         for (size_t i = 0; i < n; ++i) {
             total += pcm_len[i];
             if (validate_desc(descs[i]) == QOA_B200_OK) per_frame_step += (uint64_t)QOA_B200_FRAME_LEN * descs[i].channels;
         }
-        if (total >= (512ull << 20) && per_frame_step && (256ull << 20) / per_frame_step >= 2)
+        if (total >= 3 * enc_chunk_values() && per_frame_step && per_frame_step <= enc_chunk_values())
             return encode_all_batch_pipelined(ctx, descs, pcm, pcm_len, out, out_cap, out_len, status, n, total);
     }
     cudaStream_t s = ctx->host_stream();
@@ -743,7 +750,7 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
     }
     if (values_per_frame_step == 0) return 0;
     (void)total_pcm_values;
-    const uint32_t frames_per_chunk = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / values_per_frame_step); // ~512 MB of PCM
+    const uint32_t frames_per_chunk = (uint32_t)std::max<uint64_t>(1, enc_chunk_values() / values_per_frame_step);
     qoa_b200_encoder_batch *enc = nullptr;
     std::vector<int32_t> new_status(n);
     int rc = qoa_b200_encoder_batch_new(ctx, d.data(), n, new_status.data(), &enc);

@@ -551,7 +551,7 @@ print('variants ok')
 
 
 def test_encode_all_batch_pipelined(eng, N):
-    """Host batches above 1 GB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
+    """Host batches above ~0.5 GB of PCM are encoded in time chunks on three CUDA streams with the LMS state carried on
     the device between chunks; the bytes must equal the one-shot result (= the oracle), invalid streams included."""
     import torch
     n_streams, ch, rate, n = 62, 2, 48000, 5120 * 850 + 777
