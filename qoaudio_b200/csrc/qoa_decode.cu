@@ -1031,19 +1031,8 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
     cudaError_t e;
     if (uniform_ch == 2) {
-        // QOA_B200_DEC_VARIANT selects a tuning variant (development aid; the default is the measured best).
-        static int variant = -1;
-        if (variant < 0) {
-            const char *v = getenv("QOA_B200_DEC_VARIANT");
-            variant = v ? atoi(v) : 0;
-        }
-        switch (variant) {
-        case 1: e = launch_fast<2, 3, 1, 320>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 2: e = launch_fast<2, 3, 1, 192>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 3: e = launch_fast<2, 3, 1, 640>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        case 5: e = launch_fast<2, 3, 1, 128>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        default: e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
-        }
+        // 256 threads x 2 CTAs per SM is the measured best (128 / 192 / 288 / 320 / 640 threads: DESIGN.md section 4)
+        e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch == 1) {
         e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch >= 3 && uniform_ch <= 8) {
