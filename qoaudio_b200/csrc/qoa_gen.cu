@@ -217,7 +217,12 @@ __global__ void __launch_bounds__(512) int_issue_kernel(int *out, int iters, int
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
             }
             if (KIND == 3) QOA_OP8(asm volatile("cvt.pack.sat.s16.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
-            if (KIND == 4) QOA_OP8(asm volatile("min.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            if (KIND == 4) { // alternate min / max so that ptxas cannot fold min(min(x, a), a)
+                if (u & 1)
+                    QOA_OP8(asm volatile("min.s32 %0, %0, %1;" : "+r"(x) : "r"(b)))
+                else
+                    QOA_OP8(asm volatile("max.s32 %0, %0, %1;" : "+r"(x) : "r"(a)))
+            }
             if (KIND == 5) QOA_OP8(asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
             if (KIND == 6) QOA_OP8(asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b)))
             if (KIND == 7) QOA_OP8(asm volatile("{ .reg .s32 t; shr.s32 t, %0, 13; add.s32 %0, t, %1; }" : "+r"(x) : "r"(a)))
