@@ -22,6 +22,12 @@ def test_header_and_binding_agree():
     assert header_symbols() == sorted(N.SYMBOLS)
 
 
+def test_rust_shim_declares_the_same_symbols():
+    """rust/qoa-b200-sys (shipped as source: no rustc in this image) must bind exactly the header's entry points."""
+    src = open(os.path.join(ROOT, "rust", "qoa-b200-sys", "src", "lib.rs")).read()
+    assert sorted(set(re.findall(r"fn (qoa_b200_[a-z0-9_]+)", src))) == header_symbols()
+
+
 def test_library_exports_every_declared_symbol():
     import qoaudio_b200._native as N
     L = N.lib()
