@@ -409,11 +409,8 @@ __device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, 
 // Both channels of one sample.  The two reconstructed values are clamped to i16 AND packed into the (L, R) output
 // word by one I2IP (cvt.pack.sat.s16.s32); the clamped values are then read back out of the packed word for the LMS
 // history.  Same arithmetic as decode_step, two instructions fewer per sample pair.
-template <int I>
-__device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb)
+__device__ __forceinline__ uint32_t pair_core(Chain &a, Chain &b, int2 ta, int2 tb)
 {
-    const int2 ta = lds_v2(row_a | code_off<I>(wa.x, wa.y)); // {dequantized, delta}
-    const int2 tb = lds_v2(row_b | code_off<I>(wb.x, wb.y));
     const int xa = ((a.w0 * a.h0 + a.w1 * a.h1 + a.w2 * a.h2 + a.w3 * a.h3) >> 13) + ta.x; // predict :799-805, :310
     const int xb = ((b.w0 * b.h0 + b.w1 * b.h1 + b.w2 * b.h2 + b.w3 * b.h3) >> 13) + tb.x;
     uint32_t packed; // (clamp_i16(xb) << 16) | (clamp_i16(xa) & 0xffff)
@@ -435,6 +432,74 @@ __device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_
     b.s0 = b.s1; b.s1 = b.s2; b.s2 = b.s3; b.s3 = sign_pm1(rb);
     return packed;
 }
+
+template <int I>
+__device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb)
+{
+    const int2 ta = lds_v2(row_a | code_off<I>(wa.x, wa.y)); // {dequantized, delta}
+    const int2 tb = lds_v2(row_b | code_off<I>(wb.x, wb.y));
+    return pair_core(a, b, ta, tb);
+}
+
+// ---- two codes per lookup (stereo fast path) -------------------------------------------------------------------------
+// Entry (sf, c1, c2) = {dq(c1), dq(c1) >> 4, dq(c2), dq(c2) >> 4}, 16 bytes, four copies (lane & 3): byte
+// sf * 4096 + (c1 * 8 + c2) * 64 + (lane & 3) * 16, 64 KiB.  One SHF + LOP3 + LDS.128 serves two samples instead of two
+// SHF + LOP3 + LDS.64; the price is one CTA per SM and two-way bank conflicts on about half of the quarter-warp phases.
+constexpr int kLut2Bytes = 16 * 64 * 4 * 16;
+constexpr uint32_t kLut2Align = 4096; // bits 6..11 of the base must be zero
+
+__device__ __forceinline__ void fill_lut2(uint8_t *lut)
+{
+    int4 *v = reinterpret_cast<int4 *>(lut);
+    for (int i = threadIdx.x; i < 16 * 64 * 4; i += blockDim.x) {
+        const int sf = i >> 8, c1 = (i >> 5) & 7, c2 = (i >> 2) & 7;
+        const int d1 = c_dequant[sf * 8 + c1], d2 = c_dequant[sf * 8 + c2];
+        v[i] = make_int4(d1, d1 >> 4, d2, d2 >> 4);
+    }
+    __syncthreads();
+}
+
+// Byte offset ((c1 * 8 + c2) * 64) of the codes of samples I and I + 1 (I even).
+template <int I>
+__device__ __forceinline__ uint32_t code2_off(uint32_t hi, uint32_t lo)
+{
+    constexpr int pos = 54 - 3 * I; // LSB of the second code within the 64-bit word
+    constexpr int sh = pos - 6;     // shift that brings the six bits to bits 11..6
+    uint32_t v;
+    if constexpr (sh >= 32)
+        v = hi >> (sh - 32);
+    else if constexpr (sh > 0)
+        v = __funnelshift_r(lo, hi, sh);
+    else if constexpr (sh == 0)
+        v = lo;
+    else
+        v = lo << (-sh);
+    return v & 0xfc0u;
+}
+
+__device__ __forceinline__ int4 lds_v4(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int I>
+struct PairLoop2 {
+    static __device__ __forceinline__ void run(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb,
+                                               uint32_t *o)
+    {
+        const int4 ta = lds_v4(row_a | code2_off<I>(wa.x, wa.y));
+        const int4 tb = lds_v4(row_b | code2_off<I>(wb.x, wb.y));
+        o[I] = pair_core(a, b, make_int2(ta.x, ta.y), make_int2(tb.x, tb.y));
+        o[I + 1] = pair_core(a, b, make_int2(ta.z, ta.w), make_int2(tb.z, tb.w));
+        PairLoop2<I + 2>::run(a, b, row_a, row_b, wa, wb, o);
+    }
+};
+template <>
+struct PairLoop2<20> {
+    static __device__ __forceinline__ void run(Chain &, Chain &, uint32_t, uint32_t, uint2, uint2, uint32_t *) {}
+};
 
 template <int I>
 struct PairLoop {
@@ -567,7 +632,7 @@ __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b)
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
 
-template <int CH, int S, int NB, int THREADS>
+template <int CH, int S, int NB, int THREADS, bool P2 = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
 decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
@@ -579,10 +644,16 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kRowWords = Cfg::kOutRowBytes / 4;
     constexpr uint32_t kSliceWords = Cfg::kSliceBytes / 4;
+    static_assert(!P2 || CH == 2, "two-code lookups: stereo only");
+    constexpr int kLutBytes = P2 ? kLut2Bytes : qoa::kLutBytes;       // shadows the single-code constants below
+    constexpr uint32_t kLutAlign = P2 ? kLut2Align : qoa::kLutAlign;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
-    fill_lut(smem);
+    if (P2)
+        fill_lut2(smem);
+    else
+        fill_lut(smem);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t fi = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
 
@@ -646,7 +717,7 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
         if (CH == 2) load_lms(b, fp + 24);
     }
     uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
-    const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
+    const uint32_t lane_row = smem_u32(smem) + (P2 ? (lane & 3) * 16 : (lane & 15) * 8);
     const uint32_t warp_tiles = smem_u32(smem + kLutBytes) + (threadIdx.x >> 5) * Cfg::kWarpBytes;
     // per-warp table {PCM pointer, nsamp} of the 32 rows for the row-by-row copy path
     const uint32_t rows_meta = smem_u32(smem + kLutBytes) + (THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes) +
@@ -690,10 +761,13 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
                 const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
                 const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
                 const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
-                const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
-                const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+                const uint32_t row_a = lane_row + (wa.x >> 28) * (P2 ? 4096 : 1024); // sf = top nibble (:303)
+                const uint32_t row_b = lane_row + (wb.x >> 28) * (P2 ? 4096 : 1024);
                 uint32_t o[20];
-                PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+                if (P2)
+                    PairLoop2<0>::run(a, b, row_a, row_b, wa, wb, o);
+                else
+                    PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             } else {
@@ -995,15 +1069,64 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     }
 }
 
-template <int CH, int S, int NB, int THREADS>
+__global__ void smem_base_probe(uint32_t *out)
+{
+    extern __shared__ uint8_t probe_smem[];
+    *out = smem_u32(probe_smem);
+}
+
+// Bytes between the start of dynamic shared memory (of a kernel without static shared memory) and the next 4 KiB
+// boundary of the shared window, measured once per device; -1 if it cannot be measured.
+static int p2_pad()
+{
+    static int pad[64];
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!done[dev]) {
+        uint32_t *d = nullptr, h = 0;
+        pad[dev] = -1;
+        if (cudaMalloc(&d, sizeof h) == cudaSuccess) {
+            smem_base_probe<<<1, 1, 16>>>(d);
+            if (cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
+                pad[dev] = (int)((kLut2Align - (h & (kLut2Align - 1))) & (kLut2Align - 1));
+            cudaFree(d);
+        }
+        cudaGetLastError();
+        done[dev] = true;
+    }
+    return pad[dev];
+}
+
+// The two-code kernel runs one 512-thread CTA per SM: worth it only when the grid is many waves deep, and possible only
+// if table + tiles fit the device's opt-in shared-memory limit with the measured pad.
+constexpr uint64_t kP2MinFrames = 512ull * 148 * 8;
+static bool p2_usable()
+{
+    static const bool off = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 0; // development aid
+    if (off) return false;
+    const int pad = p2_pad();
+    if (pad < 0) return false;
+    int dev = 0, limit = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return false;
+    using Cfg = FastCfg<2, 3, 1>;
+    return (size_t)pad + kLut2Bytes + 16 * (size_t)(Cfg::kWarpBytes + Cfg::kInWarpBytes + 512) <= (size_t)limit;
+}
+
+template <int CH, int S, int NB, int THREADS, bool P2 = false>
 static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
                                const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
 {
     using Cfg = FastCfg<CH, S, NB>;
-    const size_t smem = kLutAlign + kLutBytes + (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes + 512);
+    // The two-code table needs a 4 KiB-aligned base: the pad is computed from the measured start of dynamic shared
+    // memory (p2_pad()), because 512 threads + 64 KiB only fit the 227 KiB limit with the exact pad (3072 bytes today).
+    const size_t smem = (P2 ? (size_t)p2_pad() + kLut2Bytes : kLutAlign + kLutBytes) +
+                        (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes + 512);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS>,
+        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS, P2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
@@ -1019,7 +1142,7 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
     if (const char *dbg = getenv("QOA_B200_TMAP")) use_map = std::min(use_map, atoi(dbg)); // development aid: 0 = no tensor stores, 1 = no overlapping rows
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    decode_fast_kernel<CH, S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
+    decode_fast_kernel<CH, S, NB, THREADS, P2><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
                                                                                    d_out, map, map_rem, use_map);
     return cudaGetLastError();
 }
@@ -1032,7 +1155,13 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
     cudaError_t e;
     if (uniform_ch == 2) {
         // 256 threads x 2 CTAs per SM is the measured best (128 / 192 / 288 / 320 / 640 threads: DESIGN.md section 4)
-        e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        // big batches: two codes per lookup, one 512-thread CTA per SM (+2-2.5 %); otherwise 256 threads x 2 CTAs per SM,
+        // the measured best of 128 / 192 / 256 / 288 / 320 / 640 threads
+        static const bool force_p2 = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 2; // development aid
+        if ((n_frames >= kP2MinFrames || force_p2) && p2_usable())
+            e = launch_fast<2, 3, 1, 512, true>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        else
+            e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch == 1) {
         e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch >= 3 && uniform_ch <= 8) {

@@ -517,6 +517,36 @@ def test_batch_tensor_rows_move_as_strided_copies(eng):
     assert (dec[:, n * ch:] == 77).all()                                      # nothing written past a row's samples
 
 
+@pytest.mark.parametrize("p2", ["0", "2"])
+def test_stereo_decode_kernel_variants(p2):
+    """Big stereo batches decode with two codes per table lookup (one 512-thread CTA per SM), smaller ones with one code
+    per lookup.  Both kernels are forced in turn (QOA_B200_DEC_P2 is read once per process, hence the subprocess) on
+    full frames, partial frames and slices, stream boundaries inside a warp and truncated streams."""
+    import subprocess
+    import sys
+    code = """
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/tests')
+import numpy as np, signals, qoaudio_b200
+from oracle import binding as ob
+eng = qoaudio_b200.default_engine()
+lens = [5120, 5120 * 3, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 4080, 2 * 5120 + 3082, 5120 * 40 + 119]
+enc = [ob.encode_all(signals.synth_pcm(51, i, 2, n, 'noise' if i % 3 == 1 else 'music'), 2, 44100, n)[1] for i, n in enumerate(lens)]
+streams = enc * 5 + [e[:len(e) - 11] for e in enc[:4]] + [open({root!r} + '/tests/golden/julien_baker_sprained_ankle.qoa', 'rb').read()]
+for mode in (0, 1):
+    infos, outs = eng.decode_batch(streams, mode)
+    for i, s in enumerate(streams):
+        oi, opcm = (ob.decode_iter(s)[:2] if mode == 0 else ob.decode_all(s))
+        assert infos[i]['status'] == oi['status'] and infos[i]['samples'] == oi['samples'], (mode, i)
+        assert np.array_equal(outs[i], opcm), (mode, i)
+print('variants ok')
+"""
+    from conftest import ROOT
+    env = dict(os.environ, QOA_B200_DEC_P2=p2)
+    r = subprocess.run([sys.executable, "-c", code.format(root=ROOT)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("fast", ["0", "1"])
 def test_encode_kernel_variants(fast):
     """Small batches take the latency-mode kernel (threshold search, lazily applied LMS update, exact redo of slices
