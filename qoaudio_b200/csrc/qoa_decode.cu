@@ -385,10 +385,16 @@ __device__ __forceinline__ int2 lds_v2(uint32_t addr)
 
 // One sample of one channel (:306-317).  `row` = shared address of the lane's LUT entries for this slice's
 // scalefactor (1 KiB-aligned apart from the lane offset, so OR-ing the code offset in is an add).
+__device__ __forceinline__ int step_core(Chain &c, int2 t);
+
 template <int I>
 __device__ __forceinline__ int decode_step(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
 {
-    const int2 t = lds_v2(row | code_off<I>(hi, lo));                             // {dequantized, delta}
+    return step_core(c, lds_v2(row | code_off<I>(hi, lo))); // {dequantized, delta}
+}
+
+__device__ __forceinline__ int step_core(Chain &c, int2 t)
+{
     const int p = (c.w0 * c.h0 + c.w1 * c.h1 + c.w2 * c.h2 + c.w3 * c.h3) >> 13; // predict :799-805
     const int r = clamp_i16(p + t.x);                                             // :310
     c.w0 += c.s0 * t.y;                                                           // update :821-828
@@ -501,6 +507,22 @@ struct PairLoop2<20> {
     static __device__ __forceinline__ void run(Chain &, Chain &, uint32_t, uint32_t, uint2, uint2, uint32_t *) {}
 };
 
+__device__ __forceinline__ uint32_t two_core(Chain &c, int2 t0, int2 t);
+
+template <int I>
+struct SingleLoop2 { // mono: the two codes of one lookup are two consecutive samples = one output word
+    static __device__ __forceinline__ void run(Chain &a, uint32_t row_a, uint2 wa, uint32_t *o)
+    {
+        const int4 t = lds_v4(row_a | code2_off<I>(wa.x, wa.y));
+        o[I / 2] = two_core(a, make_int2(t.x, t.y), make_int2(t.z, t.w));
+        SingleLoop2<I + 2>::run(a, row_a, wa, o);
+    }
+};
+template <>
+struct SingleLoop2<20> {
+    static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, uint32_t *) {}
+};
+
 template <int I>
 struct PairLoop {
     // Decodes samples I..19 of a slice for two channels; o[i] = (r_b << 16) | (r_a & 0xffff).
@@ -519,11 +541,17 @@ struct PairLoop<20> {
 // Two consecutive samples of ONE channel -> the output word (r1 << 16) | (r0 & 0xffff).  The second sample is clamped
 // by the same I2IP that builds the word (its other operand, r0, is already in range), so the pair costs one
 // instruction less than two clamps plus a pack.
+__device__ __forceinline__ uint32_t two_core(Chain &c, int2 t0, int2 t);
+
 template <int I>
 __device__ __forceinline__ uint32_t decode_two_steps(Chain &c, uint32_t row, uint32_t hi, uint32_t lo)
 {
-    const int r0 = decode_step<I>(c, row, hi, lo);
-    const int2 t = lds_v2(row | code_off<I + 1>(hi, lo));
+    return two_core(c, lds_v2(row | code_off<I>(hi, lo)), lds_v2(row | code_off<I + 1>(hi, lo)));
+}
+
+__device__ __forceinline__ uint32_t two_core(Chain &c, int2 t0, int2 t)
+{
+    const int r0 = step_core(c, t0);
     const int x1 = ((c.w0 * c.h0 + c.w1 * c.h1 + c.w2 * c.h2 + c.w3 * c.h3) >> 13) + t.x;
     uint32_t packed;
     asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(packed) : "r"(x1), "r"(r0));
@@ -644,7 +672,6 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kRowWords = Cfg::kOutRowBytes / 4;
     constexpr uint32_t kSliceWords = Cfg::kSliceBytes / 4;
-    static_assert(!P2 || CH == 2, "two-code lookups: stereo only");
     constexpr int kLutBytes = P2 ? kLut2Bytes : qoa::kLutBytes;       // shadows the single-code constants below
     constexpr uint32_t kLutAlign = P2 ? kLut2Align : qoa::kLutAlign;
     extern __shared__ uint8_t smem_raw[];
@@ -775,9 +802,12 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
                 const uint32_t byte = skew + 8 * k;
                 const uint2 ra = lds64(in_ring + ((byte >> 4) & 3) * 512 + (byte & 8));
                 const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
-                const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+                const uint32_t row_a = lane_row + (wa.x >> 28) * (P2 ? 4096 : 1024);
                 uint32_t o[10];
-                SingleLoop<0>::run(a, row_a, wa, o);
+                if (P2)
+                    SingleLoop2<0>::run(a, row_a, wa, o);
+                else
+                    SingleLoop<0>::run(a, row_a, wa, o);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) sts64(dst_s + i * 8, o[2 * i], o[2 * i + 1]); // 40 bytes per slice: rows stay 8-byte aligned
             }
@@ -1163,7 +1193,11 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
         else
             e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch == 1) {
-        e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        static const bool force_p2 = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 2; // development aid
+        if ((n_frames >= kP2MinFrames || force_p2) && p2_usable())
+            e = launch_fast<1, 6, 1, 512, true>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        else
+            e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch >= 3 && uniform_ch <= 8) {
         const size_t smem = kLutAlign + kLutBytes + (size_t)(kMultiThreads / 32) * (kMultiTileBytes + 2048 + 512);
         {

@@ -519,7 +519,7 @@ def test_batch_tensor_rows_move_as_strided_copies(eng):
 
 @pytest.mark.parametrize("p2", ["0", "2"])
 def test_stereo_decode_kernel_variants(p2):
-    """Big stereo batches decode with two codes per table lookup (one 512-thread CTA per SM), smaller ones with one code
+    """Big stereo and mono batches decode with two codes per table lookup (one 512-thread CTA per SM), smaller ones with one code
     per lookup.  Both kernels are forced in turn (QOA_B200_DEC_P2 is read once per process, hence the subprocess) on
     full frames, partial frames and slices, stream boundaries inside a warp and truncated streams."""
     import subprocess
@@ -533,12 +533,14 @@ eng = qoaudio_b200.default_engine()
 lens = [5120, 5120 * 3, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 4080, 2 * 5120 + 3082, 5120 * 40 + 119]
 enc = [ob.encode_all(signals.synth_pcm(51, i, 2, n, 'noise' if i % 3 == 1 else 'music'), 2, 44100, n)[1] for i, n in enumerate(lens)]
 streams = enc * 5 + [e[:len(e) - 11] for e in enc[:4]] + [open({root!r} + '/tests/golden/julien_baker_sprained_ankle.qoa', 'rb').read()]
-for mode in (0, 1):
-    infos, outs = eng.decode_batch(streams, mode)
-    for i, s in enumerate(streams):
-        oi, opcm = (ob.decode_iter(s)[:2] if mode == 0 else ob.decode_all(s))
-        assert infos[i]['status'] == oi['status'] and infos[i]['samples'] == oi['samples'], (mode, i)
-        assert np.array_equal(outs[i], opcm), (mode, i)
+mono = [ob.encode_all(signals.synth_pcm(52, i, 1, n + 1, 'noise' if i % 4 == 2 else 'music'), 1, 16000, n + 1)[1] for i, n in enumerate(lens)]
+for batch in (streams, mono * 4 + [e[:len(e) - 9] for e in mono[:3]]):   # all-stereo, then all-mono: each takes its own kernel
+    for mode in (0, 1):
+        infos, outs = eng.decode_batch(batch, mode)
+        for i, s in enumerate(batch):
+            oi, opcm = (ob.decode_iter(s)[:2] if mode == 0 else ob.decode_all(s))
+            assert infos[i]['status'] == oi['status'] and infos[i]['samples'] == oi['samples'], (mode, i)
+            assert np.array_equal(outs[i], opcm), (mode, i)
 print('variants ok')
 """
     from conftest import ROOT
