@@ -86,17 +86,10 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference(args, want_encode=True):
-    """The CPU arm: oracle (kind 'port'), one stream per thread, bounded sample of the decode (and encode) workload."""
+def cpu_decode_sample(threads):
+    """One stream of the headline shape per thread: decode cost is data-independent, so the sample is built like the
+    GPU's generator (valid headers + random payload) instead of spending minutes of CPU encode on it."""
     import numpy as np
-
-    import signals
-    from oracle import binding as ob
-    cores = os.cpu_count() or 1
-    threads = cores
-    # ---- decode sample: real encoder output of `threads` distinct 60 s streams would cost minutes of CPU encode;
-    # decode cost is data-independent, so the sample is built like the GPU's generator: valid headers + random payload.
-    n_dec = max(512, threads * 2)  # ~18 core-seconds of CPU work
     size = enc_size(DEC_CH, DEC_SAMPLES)
     rng = np.random.default_rng(1)
     proto = np.frombuffer(rng.bytes(size), dtype=np.uint8).copy()
@@ -108,16 +101,33 @@ def cpu_reference(args, want_encode=True):
         fs = 8 + 16 * DEC_CH + 8 * DEC_CH * ((flen + 19) // 20)
         hdr = (DEC_CH << 56) | (DEC_RATE << 32) | (flen << 16) | fs
         proto[8 + f * fsz:16 + f * fsz] = np.frombuffer(hdr.to_bytes(8, "big"), dtype=np.uint8)
-    batch = np.tile(proto, threads)
-    rounds = max(1, n_dec // threads)
-    out_stride = DEC_SAMPLES * DEC_CH
-    rc, _ = ob.mt_decode(batch, threads, size, out_stride, threads)  # warm-up (page faults)
-    assert rc == 0
+    return np.tile(proto, threads), size
+
+
+def cpu_decode_step(batch, size, threads, rounds):
+    """Decodes rounds x threads streams, one stream per thread; returns seconds."""
+    from oracle import binding as ob
     t0 = time.perf_counter()
     for _ in range(rounds):
-        rc, _ = ob.mt_decode(batch, threads, size, out_stride, threads)
+        rc, _ = ob.mt_decode(batch, threads, size, DEC_SAMPLES * DEC_CH, threads)
         assert rc == 0
-    dt = time.perf_counter() - t0
+    return time.perf_counter() - t0
+
+
+def cpu_reference(args, want_encode=True):
+    """The CPU arm: oracle (kind 'port'), one stream per thread, bounded sample of the decode (and encode) workload."""
+    import numpy as np
+
+    import signals
+    from oracle import binding as ob
+    cores = os.cpu_count() or 1
+    threads = cores
+    n_dec = max(512, threads * 2)  # ~18 core-seconds of CPU work
+    batch, size = cpu_decode_sample(threads)
+    rounds = max(1, n_dec // threads)
+    out_stride = DEC_SAMPLES * DEC_CH
+    cpu_decode_step(batch, size, threads, 1)  # warm-up (page faults)
+    dt = cpu_decode_step(batch, size, threads, rounds)
     dec = {"value": rounds * threads * out_stride / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
            "sample": f"{rounds * threads} streams of the headline shape (60 s stereo 44.1 kHz, synthetic payload), "
                      f"one stream per thread, {dt:.1f} s wall"}
@@ -140,25 +150,29 @@ def cpu_reference(args, want_encode=True):
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: no Rust toolchain here), all
+    host threads, W untimed + exactly K timed steps; a step is a bounded sample of the headline workload, sized so that
+    the whole run stays within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = max(1, args.steps), args.warmup
-    # each step = the bounded decode sample; keep the whole run within a few minutes
-    vals = []
-    dec = None
-    for i in range(warm + steps):
-        dec, _ = cpu_reference(args, want_encode=False)
-        if i >= warm:
-            vals.append(dec["value"])
-        if len(vals) >= 3 and i >= warm + 2:
-            break
-    v = statistics.mean(vals)
-    dec["value"] = v
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    threads = os.cpu_count() or 1
+    batch, size = cpu_decode_sample(threads)
+    per_stream = DEC_SAMPLES * DEC_CH
+    t1 = cpu_decode_step(batch, size, threads, 1)  # page faults + a first estimate of one round
+    rounds = max(1, min(512 // threads, int(120.0 / (steps + warm) / max(t1, 1e-3))))
+    for _ in range(warm):
+        cpu_decode_step(batch, size, threads, rounds)
+    times = [cpu_decode_step(batch, size, threads, rounds) for _ in range(steps)]
+    total = sum(times)
+    v = steps * rounds * threads * per_stream / total / 1e6
+    dec = {"value": v, "unit": "Msamples/s", "cores": threads, "kind": "port",
+           "sample": f"{rounds * threads} streams of the headline shape (60 s stereo 44.1 kHz, synthetic payload) per step, "
+                     f"one stream per thread, {steps} steps, {total:.1f} s wall"}
     line = {"impl": "reference", "metric": "batch decode throughput", "value": v, "unit": "Msamples/s",
-            "n_gpus": args.gpus, "steps": len(vals), "warmup": warm,
-            "ms_per_step": DEC_SAMPLES * DEC_CH * max(512, 2 * (os.cpu_count() or 1)) / v / 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": total / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": workload_config(args), "cpu_baseline": dec,
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
