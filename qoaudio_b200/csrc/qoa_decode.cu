@@ -12,6 +12,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -1145,6 +1146,19 @@ static bool p2_usable()
     return (size_t)pad + kLut2Bytes + 16 * (size_t)(Cfg::kWarpBytes + Cfg::kInWarpBytes + 512) <= (size_t)limit;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices have been configured for each kernel instantiation.
+struct PerDeviceOnce {
+    std::atomic<bool> done[64];
+    PerDeviceOnce() { for (auto &d : done) d.store(false); }
+    // returns the slot of the current device, or nullptr when it has to be configured on every launch
+    std::atomic<bool> *slot()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+        return &done[dev];
+    }
+};
+
 template <int CH, int S, int NB, int THREADS, bool P2 = false>
 static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
                                const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
@@ -1154,12 +1168,13 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
     // memory (p2_pad()), because 512 threads + 64 KiB only fit the 227 KiB limit with the exact pad (3072 bytes today).
     const size_t smem = (P2 ? (size_t)p2_pad() + kLut2Bytes : kLutAlign + kLutBytes) +
                         (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes + 512);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    std::atomic<bool> *cfg = configured.slot();
+    if (!cfg || !cfg->load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS, P2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (cfg) cfg->store(true, std::memory_order_release);
     }
     CUtensorMap map, map_rem;
     memset(&map, 0, sizeof map);
@@ -1172,8 +1187,8 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
     if (const char *dbg = getenv("QOA_B200_TMAP")) use_map = std::min(use_map, atoi(dbg)); // development aid: 0 = no tensor stores, 1 = no overlapping rows
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    decode_fast_kernel<CH, S, NB, THREADS, P2><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames, d_out_base,
-                                                                                   d_out, map, map_rem, use_map);
+    decode_fast_kernel<CH, S, NB, THREADS, P2><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames,
+                                                                                       d_out_base, d_out, map, map_rem, use_map);
     return cudaGetLastError();
 }
 
@@ -1204,11 +1219,12 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
             const uint32_t pairs = (uniform_ch + 1) / 2, rows = 32 / pairs, sl = (uniform_ch & 1) ? 2 : 1;
             if (rows * (sl * kSliceLen * uniform_ch * 2 + 16) > (uint32_t)kMultiTileBytes) return cudaErrorInvalidValue;
         }
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        std::atomic<bool> *cfg = configured.slot();
+        if (!cfg || !cfg->load(std::memory_order_acquire)) {
             e = cudaFuncSetAttribute(decode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured = true;
+            if (cfg) cfg->store(true, std::memory_order_release);
         }
         const uint32_t fpw = 32 / ((uniform_ch + 1) / 2);
         const uint64_t warps = (n_frames + fpw - 1) / fpw;
