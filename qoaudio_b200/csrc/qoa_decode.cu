@@ -451,7 +451,10 @@ __device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_
 // ---- two codes per lookup (stereo fast path) -------------------------------------------------------------------------
 // Entry (sf, c1, c2) = {dq(c1), dq(c1) >> 4, dq(c2), dq(c2) >> 4}, 16 bytes, four copies (lane & 3): byte
 // sf * 4096 + (c1 * 8 + c2) * 64 + (lane & 3) * 16, 64 KiB.  One SHF + LOP3 + LDS.128 serves two samples instead of two
-// SHF + LOP3 + LDS.64; the price is one CTA per SM and two-way bank conflicts on about half of the quarter-warp phases.
+// SHF + LOP3 + LDS.64; the price is one CTA per SM and two-way bank conflicts on almost every load (lanes l and l + 4 of
+// a quarter-warp share a copy).  Eight copies (128 KiB, conflict-free: 58 M conflicts instead of 499 M) only fit next to
+// one-slice (80-byte) staging rows, and those are bound by the TMA engine's row rate (~10 cycles per box row per SM):
+// 36.0 ms against 27.2 ms for the headline batch (round 2, profiles/r02_decode_two_code_8_copies_ncu.txt).
 constexpr int kLut2Bytes = 16 * 64 * 4 * 16;
 constexpr uint32_t kLut2Align = 4096; // bits 6..11 of the base must be zero
 
