@@ -118,9 +118,10 @@ int qoa_b200_encode_all_batch(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, con
                               const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap, size_t *out_len,
                               int32_t *status, size_t n);
 
-/* Same, payload resident on the device.  d_pcm/d_out are device arenas; pcm_off[i] (in i16 elements, even) and
- * out_off[i] (in bytes, multiple of 8) are HOST arrays locating stream i.  Validation as above (pcm_len/out_cap
- * are HOST arrays).  Enqueues on `stream` (cudaStream_t) and returns without synchronising. */
+/* Same, payload resident on the device.  d_pcm/d_out are device arenas (d_out 8-byte aligned, else QOA_B200_E_ARG);
+ * pcm_off[i] (in i16 elements, even) and out_off[i] (in bytes, multiple of 8) are HOST arrays locating stream i.
+ * Validation as above (pcm_len/out_cap are HOST arrays).  Enqueues on `stream` (cudaStream_t) and returns without
+ * synchronising. */
 int qoa_b200_encode_all_batch_dev(qoa_b200_ctx *ctx, const qoa_b200_desc *descs, const int16_t *d_pcm,
                                   const uint64_t *pcm_off, const size_t *pcm_len, uint8_t *d_out,
                                   const uint64_t *out_off, const size_t *out_cap, size_t *out_len, int32_t *status,
@@ -175,7 +176,10 @@ typedef struct qoa_b200_decode_plan qoa_b200_decode_plan;
 /* HOST input: copies the n streams to the device, indexes them.  Synchronises. */
 int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
                                 int mode, qoa_b200_decode_plan **plan);
-/* DEVICE input: stream i occupies d_qoa[in_off[i] .. in_off[i]+len[i]) (in_off multiple of 16; HOST arrays).
+/* DEVICE input: stream i occupies d_qoa[in_off[i] .. in_off[i]+len[i]) (d_qoa 16-byte aligned and in_off a multiple
+ * of 16, else QOA_B200_E_ARG; HOST arrays).  The decode kernels read the arena in 16-byte vectors: the bytes up to the
+ * next 16-byte boundary behind a stream's end must be readable (any content; they are never interpreted) — true for
+ * every stream but possibly the last of an arena that ends exactly at in_off + len with len % 16 == 8.
  * Runs the index kernels on `stream` and synchronises it (the per-stream info is needed on the host). */
 int qoa_b200_decode_plan_create_dev(qoa_b200_ctx *ctx, const uint8_t *d_qoa, const uint64_t *in_off,
                                     const size_t *len, size_t n, int mode, void *stream,
@@ -190,8 +194,9 @@ size_t qoa_b200_decode_plan_frame_headers(const qoa_b200_decode_plan *plan, size
  * DEC_OUTPUT_TOO_SMALL (nothing is written for that stream).  Synchronises. */
 int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *const *out, const size_t *out_cap,
                              int32_t *status);
-/* Decode into a DEVICE arena: stream i goes to d_out + out_off[i] (i16 elements, multiple of 8; HOST array).
- * Enqueues on `stream`; no synchronisation. */
+/* Decode into a DEVICE arena: stream i goes to d_out + out_off[i] (i16 elements; HOST array).  The fast kernels need
+ * 16-byte aligned stream slots (d_out 16-byte aligned and out_off a multiple of 8); streams whose slot is not take
+ * the generic kernel (correct, ~5x slower).  Enqueues on `stream`; no synchronisation. */
 int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t *d_out, const uint64_t *out_off,
                                  const size_t *out_cap, int32_t *status, void *stream);
 

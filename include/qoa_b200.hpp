@@ -265,6 +265,7 @@ public:
         if (!writer.write(reinterpret_cast<const char *>(h), 8)) throw EncodeError(EncodeError::IoError, "write failed");
     }
 
+    // Returns frame_len, the samples per channel encoded (Ok(frame_len), :438).
     size_t encode_frame(const std::vector<int16_t> &sample_data, std::ostream &writer) // :418-439
     {
         std::vector<uint8_t> out(qoa_b200_frame_size(desc_.channels, QOA_FRAME_LEN));
@@ -279,7 +280,7 @@ public:
         if (status != QOA_B200_OK) throw EncodeError(static_cast<EncodeError::Kind>(status));
         if (!writer.write(reinterpret_cast<const char *>(out.data()), std::streamsize(written)))
             throw EncodeError(EncodeError::IoError, "write failed");
-        return written;
+        return sample_data.size() / desc_.channels;
     }
 
 private:

@@ -171,7 +171,7 @@ class QoaEncoder:
         writer.write(b"qoaf" + int(s).to_bytes(4, "big"))
 
     def encode_frame(self, sample_data, writer):
-        """src/lib.rs:418-439; returns the number of bytes written."""
+        """src/lib.rs:418-439; returns frame_len, the samples per channel encoded (Ok(frame_len), :438)."""
         pcm = _as_pcm(sample_data)
         st, outs = self._state().encode_frame([pcm])
         if st[0] != N.OK:
@@ -180,7 +180,7 @@ class QoaEncoder:
             writer.write(outs[0])
         except OSError as e:
             raise EncodeError("IoError", str(e))
-        return len(outs[0])
+        return pcm.size // self._desc.channels
 
 
 class QoaEncoderBatch:

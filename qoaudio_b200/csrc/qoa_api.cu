@@ -27,6 +27,7 @@ struct PoolBlock {
     void *ptr;
     size_t size;
     bool free;
+    int slot = 0; // while a pipelined host call runs: the pipeline stream (1..3) whose earlier stage last used the block
 };
 
 } // namespace
@@ -39,10 +40,34 @@ struct qoa_b200_ctx {
     std::vector<PoolBlock> pool;
     cudaStream_t last_stream = nullptr;
     bool used = false;
-    // pipelined host calls: several internal streams are in flight at once, so scratch blocks are only returned to
-    // the pool when the whole call has drained
+    // Pipelined host calls keep three internal streams in flight.  A block released by a stage that was enqueued on
+    // pipeline stream k is parked in deferred[k] and handed out again only to LATER stages of the same stream (stream
+    // order makes that safe without waiting), so a call needs the arenas of about three stages, not of the whole batch.
     bool pipelining = false;
-    std::vector<void *> deferred;
+    int cur_slot = 0;
+    std::vector<void *> deferred[4];
+    void begin_stage(int slot) // slot = 1..3: the stage about to be enqueued runs on pipe_streams[slot - 1]
+    {
+        cur_slot = slot;
+        for (void *p : deferred[slot])
+            for (auto &b : pool)
+                if (b.ptr == p) {
+                    b.free = true;
+                    b.slot = slot;
+                    break;
+                }
+        deferred[slot].clear();
+    }
+    void end_pipeline() // every pipeline stream has been synchronised
+    {
+        pipelining = false;
+        cur_slot = 0;
+        for (auto &d : deferred) {
+            for (void *p : d) release(p);
+            d.clear();
+        }
+        for (auto &b : pool) b.slot = 0;
+    }
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
     // host-mapped (pinned) result slots the index kernels write directly: one region per pipeline stream
     struct Mapped {
@@ -77,7 +102,9 @@ struct qoa_b200_ctx {
         if (bytes == 0) bytes = 16;
         PoolBlock *best = nullptr;
         for (auto &b : pool)
-            if (b.free && b.size >= bytes && b.size <= bytes * 2 + 4096 && (!best || b.size < best->size)) best = &b;
+            if (b.free && b.size >= bytes && b.size <= bytes * 2 + 4096 && (!best || b.size < best->size) &&
+                (!pipelining || b.slot == 0 || b.slot == cur_slot))
+                best = &b;
         if (best) {
             best->free = false;
             return best->ptr;
@@ -87,7 +114,7 @@ struct qoa_b200_ctx {
             // drop cached free blocks and retry once
             cudaGetLastError();
             for (auto &b : pool)
-                if (b.free && b.ptr) {
+                if (b.free && b.ptr && (!pipelining || b.slot == 0 || b.slot == cur_slot)) { // not in use by another stream
                     cudaFree(b.ptr);
                     b.ptr = nullptr;
                 }
@@ -98,14 +125,14 @@ struct qoa_b200_ctx {
                 return nullptr;
             }
         }
-        pool.push_back({p, bytes, false});
+        pool.push_back({p, bytes, false, 0});
         return p;
     }
     void release(void *p)
     {
         if (!p) return;
         if (pipelining) {
-            deferred.push_back(p);
+            deferred[cur_slot].push_back(p);
             return;
         }
         for (auto &b : pool)
@@ -399,6 +426,10 @@ extern "C" int qoa_b200_encode_all_batch_dev(qoa_b200_ctx *ctx, const qoa_b200_d
         ctx->err = "null argument";
         return QOA_B200_E_ARG;
     }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 7) || (reinterpret_cast<uintptr_t>(d_pcm) & 1)) { // 8-byte slice stores
+        ctx->err = "d_out must be 8-byte aligned and d_pcm 2-byte aligned";
+        return QOA_B200_E_ARG;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->enter(s);
@@ -595,6 +626,10 @@ extern "C" int qoa_b200_encoder_batch_encode_chunk_dev(qoa_b200_encoder_batch *e
         ctx->err = "null argument";
         return QOA_B200_E_ARG;
     }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 7) || (reinterpret_cast<uintptr_t>(d_pcm) & 1)) { // 8-byte slice stores
+        ctx->err = "d_out must be 8-byte aligned and d_pcm 2-byte aligned";
+        return QOA_B200_E_ARG;
+    }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->enter(s);
@@ -746,7 +781,7 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
         }
         out_len[i] = need;
         values_per_frame_step += (uint64_t)QOA_B200_FRAME_LEN * descs[i].channels;
-        max_frames = std::max<uint32_t>(max_frames, (descs[i].samples + QOA_B200_FRAME_LEN - 1) / QOA_B200_FRAME_LEN);
+        max_frames = std::max<uint32_t>(max_frames, (uint32_t)(((uint64_t)descs[i].samples + QOA_B200_FRAME_LEN - 1) / QOA_B200_FRAME_LEN));
     }
     if (values_per_frame_step == 0) return 0;
     (void)total_pcm_values;
@@ -774,6 +809,7 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
             }
     for (uint32_t f0 = 0, t = 0; f0 < max_frames && rc == 0; f0 += frames_per_chunk, ++t) {
         cudaStream_t s = ctx->pipe_streams[t % 3];
+        ctx->begin_stage((int)(t % 3) + 1); // the arenas of chunk t - 3 (same stream) become reusable
         uint64_t pcm_total = 0, out_total = 0;
         for (size_t i = 0; i < n; ++i) {
             chunk[i] = 0;
@@ -793,8 +829,8 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
             rc = QOA_B200_E_NOMEM;
             break;
         }
-        ctx->deferred.push_back(d_pcm);
-        ctx->deferred.push_back(d_out);
+        ctx->release(d_pcm); // parked until the next stage on this stream
+        ctx->release(d_out);
         cudaError_t e = cudaSuccess;
         Scratch sc(ctx);
         std::vector<CopyItem> items;
@@ -846,9 +882,7 @@ static int encode_all_batch_pipelined(qoa_b200_ctx *ctx, const qoa_b200_desc *de
         }
     }
     for (auto ev : events) cudaEventDestroy(ev);
-    ctx->pipelining = false;
-    for (void *p : ctx->deferred) ctx->release(p);
-    ctx->deferred.clear();
+    ctx->end_pipeline();
     qoa_b200_encoder_batch_free(enc);
     return rc;
 }
@@ -973,6 +1007,10 @@ extern "C" int qoa_b200_decode_plan_create_dev(qoa_b200_ctx *ctx, const uint8_t 
     }
     if (mode < QOA_B200_DECODE_ITER || mode > QOA_B200_DECODE_FRAMES) {
         ctx->err = "bad decode mode";
+        return QOA_B200_E_ARG;
+    }
+    if (n && (reinterpret_cast<uintptr_t>(d_qoa) & 15)) { // the kernels read the arena with 16-byte vectors
+        ctx->err = "d_qoa must be 16-byte aligned";
         return QOA_B200_E_ARG;
     }
     for (size_t i = 0; i < n; ++i)
@@ -1104,6 +1142,12 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     Scratch sc(ctx);
     std::vector<uint64_t> base(n);
     bool cls_aligned[9] = {true, true, true, true, true, true, true, true, true};
+    if (reinterpret_cast<uintptr_t>(d_out) & 15) // the fast kernels store 16-byte rows: a misaligned arena (e.g. a view with
+        for (bool &a : cls_aligned) a = false;   // a storage offset) takes the generic kernel, which stores single samples
+    if (reinterpret_cast<uintptr_t>(d_out) & 1) {
+        ctx->err = "d_out must be 2-byte aligned";
+        return QOA_B200_E_ARG;
+    }
     uint64_t out_bytes = 0;
     for (size_t i = 0; i < n; ++i) {
         int st = plan->info[i].status;
@@ -1231,6 +1275,12 @@ extern "C" int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const
         uint64_t bytes = 0;
         while (e < n && (e == b || bytes + len[e] <= kChunkBytes)) bytes += len[e++];
         cudaStream_t s = ctx->pipe_streams[c % 3];
+        ctx->cur_slot = c % 3 + 1;
+        if (c >= 3) { // the plan of chunk c - 3 ran on this stream: its arenas are reusable by this chunk (stream order)
+            qoa_b200_decode_plan_destroy(plans[c - 3]);
+            plans[c - 3] = nullptr;
+        }
+        ctx->begin_stage(c % 3 + 1);
         qoa_b200_decode_plan *plan = nullptr;
         rc = plan_create_host(ctx, qoa + b, len + b, e - b, mode, s, &plan);
         if (rc != 0) break;
@@ -1247,10 +1297,9 @@ extern "C" int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const
             rc = QOA_B200_E_CUDA;
         }
     }
-    for (auto *p : plans) qoa_b200_decode_plan_destroy(p);
-    ctx->pipelining = false;
-    for (void *p : ctx->deferred) ctx->release(p);
-    ctx->deferred.clear();
+    for (auto *p : plans)
+        if (p) qoa_b200_decode_plan_destroy(p);
+    ctx->end_pipeline();
     return rc;
 }
 

@@ -68,13 +68,13 @@ int main(int argc, char **argv)
         QoaEncoder enc(desc);
         std::ostringstream os;
         enc.write_header(os);
-        size_t total = 8;
+        size_t total = 0; // encode_frame returns Ok(frame_len) = samples per channel (src/lib.rs:438)
         for (size_t at = 0; at < pcm.size(); at += size_t(QOA_FRAME_LEN) * 2) {
             const size_t end = std::min(pcm.size(), at + size_t(QOA_FRAME_LEN) * 2);
             total += enc.encode_frame(std::vector<int16_t>(pcm.begin() + at, pcm.begin() + end), os);
         }
         const std::string s = os.str();
-        CHECK(total == one_shot.size());
+        CHECK(total == desc.samples);
         CHECK(std::vector<uint8_t>(s.begin(), s.end()) == one_shot);
         CHECK(kind_of<EncodeError>([&] { enc.encode_frame({}, os); }) == EncodeError::InvalidSamples);        // :424
         CHECK(kind_of<EncodeError>([&] { enc.encode_frame(std::vector<int16_t>(3), os); }) == EncodeError::InvalidSamples);

@@ -10,6 +10,12 @@ The fixture julien_baker_sprained_ankle.qoa is the reference's own decode fixtur
 (/root/reference/fixtures/, used by src/lib.rs:996 and benches/qoa_benchmarks.rs:3), copied as test data.
 
 Run from the repo root:  python tests/golden/make_golden.py
+
+Pinning the oracle to the crate itself (needs a Rust toolchain, which this image lacks — rust/golden-dump/ is the
+30-line program that runs the crate):
+    python tests/golden/make_golden.py --export-inputs DIR      # KATs, synthetic streams, edge signals, the fixture
+    cargo run --release --manifest-path rust/golden-dump/Cargo.toml -- DIR OUT
+    python tests/golden/make_golden.py --check-against OUT      # crate bytes == oracle bytes == golden.json
 """
 import hashlib
 import json
@@ -86,5 +92,54 @@ def main():
     print("wrote golden.json")
 
 
+def parity_inputs():
+    """name -> (pcm int16, channels, rate, samples): everything whose encoder output the oracle vouches for."""
+    inputs = dict(signals.kat_signals())
+    for kind in ("music", "noise"):
+        for (seed, stream, ch, n) in [(1, 0, 2, 12345), (2, 17, 1, 5121), (3, 5, 8, 777)]:
+            inputs[f"synth_{kind}_{seed}_{stream}_{ch}_{n}"] = (signals.synth_pcm(seed, stream, ch, n, kind), ch, 44100, n)
+    for name, sig in signals.edge_signals().items():
+        inputs[f"edge_{name}"] = (sig, 1, 8000, sig.size)
+    return inputs
+
+
+def export_inputs(out_dir):
+    os.makedirs(out_dir, exist_ok=True)
+    for name, (sig, ch, rate, n) in parity_inputs().items():
+        np.asarray(sig, dtype="<i2").tofile(os.path.join(out_dir, name + ".pcm"))
+        with open(os.path.join(out_dir, name + ".desc"), "w") as f:
+            f.write(f"{ch} {rate} {n}\n")
+    fixture = open(os.path.join(ROOT, "tests/golden/julien_baker_sprained_ankle.qoa"), "rb").read()
+    with open(os.path.join(out_dir, "fixture.qoa"), "wb") as f:
+        f.write(fixture)
+    print(f"exported {len(parity_inputs())} PCM inputs + the fixture to {out_dir}")
+
+
+def check_against(crate_dir):
+    """Compares what rust/golden-dump wrote (the reference crate's own output) with the oracle, byte for byte."""
+    bad = 0
+    for name, (sig, ch, rate, n) in parity_inputs().items():
+        st, enc = ob.encode_all(sig, ch, rate, n)
+        crate = open(os.path.join(crate_dir, name + ".qoa"), "rb").read()
+        crate_dec = np.fromfile(os.path.join(crate_dir, name + ".dec.pcm"), dtype="<i2")
+        ok = st == 0 and crate == bytes(enc) and np.array_equal(crate_dec, ob.decode_all(bytes(enc))[1])
+        bad += not ok
+        print(f"{'ok      ' if ok else 'MISMATCH'} {name}")
+    fixture = open(os.path.join(ROOT, "tests/golden/julien_baker_sprained_ankle.qoa"), "rb").read()
+    dec = np.fromfile(os.path.join(crate_dir, "fixture.decoded.pcm"), dtype="<i2")
+    re_enc = open(os.path.join(crate_dir, "fixture.reencoded.qoa"), "rb").read()
+    ok = (np.array_equal(dec, ob.decode_all(fixture)[1]) and sha(dec.tobytes()) == APPENDIX_B["fixture_decoded_pcm_sha256"]
+          and sha(re_enc) == APPENDIX_B["fixture_reencode_sha256"])
+    bad += not ok
+    print(f"{'ok      ' if ok else 'MISMATCH'} fixture decode + re-encode")
+    print("oracle PINNED to the crate" if not bad else f"{bad} mismatches: the oracle is NOT the crate")
+    return 1 if bad else 0
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) == 3 and sys.argv[1] == "--export-inputs":
+        export_inputs(sys.argv[2])
+    elif len(sys.argv) == 3 and sys.argv[1] == "--check-against":
+        sys.exit(check_against(sys.argv[2]))
+    else:
+        main()

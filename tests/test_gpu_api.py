@@ -129,10 +129,10 @@ def test_streaming_encode(q, fixture_bytes):
     enc = q.QoaEncoder(desc)
     out = io.BytesIO()
     enc.write_header(out)
-    total = 8
+    total = 0
     for i in range(0, len(pcm), 5120 * 2):
-        total += enc.encode_frame(pcm[i:i + 5120 * 2], out)
-    assert out.getvalue() == one_shot and total == len(one_shot)
+        total += enc.encode_frame(pcm[i:i + 5120 * 2], out)  # Ok(frame_len): samples per channel (src/lib.rs:438)
+    assert out.getvalue() == one_shot and total == n
     with pytest.raises(q.EncodeError):
         enc.encode_frame(np.zeros(3, np.int16), io.BytesIO())
 
