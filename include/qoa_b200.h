@@ -205,6 +205,37 @@ int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const *qoa, cons
                               int16_t *const *out, const size_t *out_cap, qoa_b200_stream_info *info,
                               int32_t *status);
 
+/* ---- several GPUs from one process --------------------------------------------------------------------------- */
+
+/* A multi-device context: one qoa_b200_ctx per listed device (devices == NULL or n <= 0: every visible device).
+ * The batch calls below cut the batch into contiguous ranges of streams, one per device, balanced by work
+ * (qoa_b200_partition), and run the single-device host path on every range from its own host thread: no collective
+ * (the path has no cross-stream dependency, src/lib.rs:59-68, :85-91), results in caller order.  This is the call a
+ * user of encode_all (src/lib.rs:760) / decode_all (:713) makes for a batch on an 8-GPU box. */
+typedef struct qoa_b200_mctx qoa_b200_mctx;
+int qoa_b200_ctx_create_multi(const int *devices, int n, qoa_b200_mctx **mctx);
+void qoa_b200_mctx_destroy(qoa_b200_mctx *mctx);
+int qoa_b200_mctx_device_count(const qoa_b200_mctx *mctx);
+/* CUDA device index / single-device context of slot i (the *_dev calls of a slot's context work as usual). */
+int qoa_b200_mctx_device(const qoa_b200_mctx *mctx, int i);
+qoa_b200_ctx *qoa_b200_mctx_ctx(qoa_b200_mctx *mctx, int i);
+/* Message of the last failing call ("device D: ..."); mctx == NULL: why ctx_create_multi failed on this thread. */
+const char *qoa_b200_mctx_last_error(const qoa_b200_mctx *mctx);
+uint64_t qoa_b200_mctx_kernel_launches(const qoa_b200_mctx *mctx);
+/* Splits range(n) into `parts` contiguous ranges of near-equal summed weight: range p = first[p] .. first[p + 1]
+ * (parts + 1 entries, ranges may be empty).  Host arithmetic only.  The batch calls weigh a stream by
+ * samples x channels (encode) or by its encoded length (decode). */
+int qoa_b200_partition(const uint64_t *weight, size_t n, int parts, size_t *first);
+int qoa_b200_mctx_partition(const qoa_b200_mctx *mctx, const uint64_t *weight, size_t n, size_t *first);
+/* qoa_b200_encode_all_batch / qoa_b200_decode_all_batch over every device of the context; same arguments, same
+ * per-stream status values, same bytes. */
+int qoa_b200_mctx_encode_all_batch(qoa_b200_mctx *mctx, const qoa_b200_desc *descs, const int16_t *const *pcm,
+                                   const size_t *pcm_len, uint8_t *const *out, const size_t *out_cap, size_t *out_len,
+                                   int32_t *status, size_t n);
+int qoa_b200_mctx_decode_all_batch(qoa_b200_mctx *mctx, const uint8_t *const *qoa, const size_t *len, size_t n,
+                                   int mode, int16_t *const *out, const size_t *out_cap, qoa_b200_stream_info *info,
+                                   int32_t *status);
+
 /* ---- synthetic workload generators (bench + tests; same integer recipes as tests/signals.py) ------------- */
 
 /* Fills d_pcm with `n_streams` streams of `channels` x `samples` interleaved i16 starting at sample index

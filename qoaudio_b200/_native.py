@@ -65,6 +65,17 @@ SYMBOLS = {
     "qoa_b200_gen_qoa_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_uint64, _P]),
     "qoa_b200_int_issue_peak": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "qoa_b200_ctx_create_multi": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "qoa_b200_mctx_destroy": (None, [_P]),
+    "qoa_b200_mctx_device_count": (C.c_int, [_P]),
+    "qoa_b200_mctx_device": (C.c_int, [_P, C.c_int]),
+    "qoa_b200_mctx_ctx": (_P, [_P, C.c_int]),
+    "qoa_b200_mctx_last_error": (C.c_char_p, [_P]),
+    "qoa_b200_mctx_kernel_launches": (C.c_uint64, [_P]),
+    "qoa_b200_partition": (C.c_int, [_P, _SZ, C.c_int, _P]),
+    "qoa_b200_mctx_partition": (C.c_int, [_P, _P, _SZ, _P]),
+    "qoa_b200_mctx_encode_all_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ]),
+    "qoa_b200_mctx_decode_all_batch": (C.c_int, [_P, _P, _P, _SZ, C.c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

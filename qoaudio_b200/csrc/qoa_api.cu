@@ -21,7 +21,7 @@ using namespace qoa;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error; // qoa_b200_last_error(NULL): why the last ctx_create of THIS thread failed
 
 struct PoolBlock {
     void *ptr;

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "qoa_kernels.h"
 
@@ -881,9 +882,8 @@ static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint3
                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static EncodeFn encode = nullptr;
-    static bool looked_up = false;
-    if (!looked_up) {
-        looked_up = true;
+    static std::once_flag looked_up; // contexts on different host threads (qoa_b200_mctx) may get here at the same time
+    std::call_once(looked_up, [] {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
@@ -891,7 +891,7 @@ static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint3
             encode = reinterpret_cast<EncodeFn>(fn);
         else
             cudaGetLastError();
-    }
+    });
     if (!encode || (reinterpret_cast<uintptr_t>(d_out) & 15) || out_bytes == 0) return 0;
     const uint64_t rows = (out_bytes + row_bytes - 1) / row_bytes + 1;
     if (rows > 0x7fffffffull) return 0;
@@ -1115,6 +1115,8 @@ static int p2_pad()
 {
     static int pad[64];
     static bool done[64] = {false};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
     if (!done[dev]) {

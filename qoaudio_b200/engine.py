@@ -58,6 +58,16 @@ class Engine:
             N.lib().qoa_b200_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
+    # the native entry points behind encode_all_batch / decode_all_batch (MultiEngine swaps in the multi-device ones)
+    def _encode_all_fn(self):
+        return N.lib().qoa_b200_encode_all_batch
+
+    def _decode_all_fn(self):
+        return N.lib().qoa_b200_decode_all_batch
+
+    def _check(self, rc, what):
+        N.check(self._h, rc, "qoa_b200_" + what)
+
     def __del__(self):
         try:
             self.close()
@@ -87,11 +97,11 @@ class Engine:
             outs.append(np.empty(N.lib().qoa_b200_encoded_size(c, s) if ok else 0, dtype=np.uint8))
         out_len = (C.c_size_t * n)()
         status = (C.c_int32 * n)()
-        rc = N.lib().qoa_b200_encode_all_batch(
+        rc = self._encode_all_fn()(
             self._h, _descs(descs), k.arr([p.ctypes.data if p.size else None for p in pcm], C.c_void_p),
             k.arr([p.size for p in pcm], C.c_size_t), k.arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p),
             k.arr([o.size for o in outs], C.c_size_t), out_len, status, n)
-        N.check(self._h, rc, "qoa_b200_encode_all_batch")
+        self._check(rc, "encode_all_batch")
         return list(status), [o[:out_len[i]] for i, o in enumerate(outs)]
 
     # ---- encode, device buffers -----------------------------------------------------------------------------
@@ -144,12 +154,12 @@ class Engine:
         info = np.zeros(n, dtype=INFO_DTYPE)
         status = np.zeros(n, dtype=np.int32)
         k = _Keep()
-        rc = N.lib().qoa_b200_decode_all_batch(
+        rc = self._decode_all_fn()(
             self._h, k.arr([b.ctypes.data if b.size else None for b in bufs], C.c_void_p),
             k.arr([b.size for b in bufs], C.c_size_t), n, mode,
             k.arr([o.ctypes.data if o.size else None for o in outs], C.c_void_p), k.arr([o.size for o in outs], C.c_size_t),
             C.c_void_p(info.ctypes.data), C.c_void_p(status.ctypes.data))
-        N.check(self._h, rc, "qoa_b200_decode_all_batch")
+        self._check(rc, "decode_all_batch")
         return info, status, outs
 
     # ---- generators / microbenchmarks --------------------------------------------------------------------------
@@ -351,6 +361,65 @@ class DecodePlan:
 
 _default = None
 _lock = threading.Lock()
+
+
+class MultiEngine(Engine):
+    """Owns a qoa_b200_mctx: several GPUs driven from this process.  encode_all_batch / decode_all_batch have the
+    single-device signatures and results; the batch is cut into contiguous ranges of streams, one per device, balanced
+    by work (qoa_b200_partition), no collective.  `engine(i)` exposes slot i's single-device context for the *_dev
+    calls."""
+
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        rc = N.lib().qoa_b200_ctx_create_multi(arr, len(devices) if devices else 0, C.byref(self._h))
+        if rc != 0:
+            msg = N.lib().qoa_b200_mctx_last_error(None)
+            raise N.NativeError(f"qoa_b200_ctx_create_multi({devices}) failed with {rc}: {msg.decode()} "
+                                "(qoaudio_b200 has no CPU fallback)")
+        self.devices = [N.lib().qoa_b200_mctx_device(self._h, i) for i in range(N.lib().qoa_b200_mctx_device_count(self._h))]
+        self.device = self.devices[0]
+
+    def close(self):
+        if self._h:
+            N.lib().qoa_b200_mctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def kernel_launches(self):
+        return int(N.lib().qoa_b200_mctx_kernel_launches(self._h))
+
+    def _encode_all_fn(self):
+        return N.lib().qoa_b200_mctx_encode_all_batch
+
+    def _decode_all_fn(self):
+        return N.lib().qoa_b200_mctx_decode_all_batch
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = N.lib().qoa_b200_mctx_last_error(self._h)
+            raise N.NativeError(f"qoa_b200_mctx_{what} failed with {rc}: {msg.decode() if msg else '?'}")
+
+    def partition(self, weights):
+        """The contiguous split the batch calls use: [(begin, end), ...] per device."""
+        return partition(weights, len(self.devices))
+
+    def engine(self, i):
+        """A borrowed single-device Engine view of slot i (do not close it)."""
+        e = Engine.__new__(Engine)
+        e.device = self.devices[i]
+        e._h = C.c_void_p(N.lib().qoa_b200_mctx_ctx(self._h, i))
+        e.close = lambda: None
+        return e
+
+
+def partition(weights, parts):
+    """qoa_b200_partition: contiguous ranges of near-equal summed weight, [(begin, end), ...] (host arithmetic only)."""
+    w = np.ascontiguousarray(weights, dtype=np.uint64)
+    first = np.zeros(parts + 1, dtype=np.uint64)
+    rc = N.lib().qoa_b200_partition(C.c_void_p(w.ctypes.data), w.size, parts, C.c_void_p(first.ctypes.data))
+    if rc != 0:
+        raise ValueError(f"qoa_b200_partition failed with {rc}")
+    return [(int(first[p]), int(first[p + 1])) for p in range(parts)]
 
 
 def default_engine():

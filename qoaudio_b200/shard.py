@@ -9,20 +9,11 @@ import os
 
 def partition_contiguous(costs, world_size):
     """Splits range(len(costs)) into `world_size` contiguous ranges whose summed costs are as even as a single
-    left-to-right sweep can make them.  Returns [(begin, end), ...] (end exclusive); ranges may be empty."""
-    n = len(costs)
-    total = float(sum(costs))
-    bounds = [0]
-    acc = 0.0
-    i = 0
-    for r in range(1, world_size):
-        target = total * r / world_size
-        while i < n and acc + costs[i] / 2.0 <= target:
-            acc += costs[i]
-            i += 1
-        bounds.append(i)
-    bounds.append(n)
-    return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
+    left-to-right sweep can make them.  Returns [(begin, end), ...] (end exclusive); ranges may be empty.
+    This is qoa_b200_partition of the C ABI: the split qoa_b200_mctx uses inside one process is the split the ranks
+    of a torchrun job use (bench.py --scaling strong)."""
+    from .engine import partition
+    return partition([max(int(c), 0) for c in costs], world_size)
 
 
 def decode_cost(qoa_len):

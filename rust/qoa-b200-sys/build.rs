@@ -8,7 +8,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
-    for src in ["qoa_api.cu", "qoa_decode.cu", "qoa_encode.cu", "qoa_gen.cu"] {
+    for src in ["qoa_api.cu", "qoa_decode.cu", "qoa_encode.cu", "qoa_gen.cu", "qoa_multi.cu"] {
         let obj = out.join(src.replace(".cu", ".o"));
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c"])

@@ -20,6 +20,7 @@ pub const QOA_B200_DECODE_FRAMES: c_int = 2;
 #[repr(C)] pub struct qoa_b200_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qoa_b200_encoder_batch { _p: [u8; 0] }
 #[repr(C)] pub struct qoa_b200_decode_plan { _p: [u8; 0] }
+#[repr(C)] pub struct qoa_b200_mctx { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)]
 pub struct qoa_b200_desc { pub channels: u32, pub sample_rate: u32, pub samples: u32 }
@@ -78,4 +79,20 @@ extern "C" {
     pub fn qoa_b200_gen_qoa_dev(ctx: *mut qoa_b200_ctx, d_qoa: *mut u8, stride: u64, n_streams: u64, first_stream: u64,
         channels: u32, sample_rate: u32, samples: u32, seed: u64, stream: *mut c_void) -> c_int;
     pub fn qoa_b200_int_issue_peak(ctx: *mut qoa_b200_ctx, kind: c_int, thread_ops_per_s: *mut f64) -> c_int;
+    // several GPUs from one process (batches sharded by stream, no collective)
+    pub fn qoa_b200_ctx_create_multi(devices: *const c_int, n: c_int, mctx: *mut *mut qoa_b200_mctx) -> c_int;
+    pub fn qoa_b200_mctx_destroy(mctx: *mut qoa_b200_mctx);
+    pub fn qoa_b200_mctx_device_count(mctx: *const qoa_b200_mctx) -> c_int;
+    pub fn qoa_b200_mctx_device(mctx: *const qoa_b200_mctx, i: c_int) -> c_int;
+    pub fn qoa_b200_mctx_ctx(mctx: *mut qoa_b200_mctx, i: c_int) -> *mut qoa_b200_ctx;
+    pub fn qoa_b200_mctx_last_error(mctx: *const qoa_b200_mctx) -> *const c_char;
+    pub fn qoa_b200_mctx_kernel_launches(mctx: *const qoa_b200_mctx) -> u64;
+    pub fn qoa_b200_partition(weight: *const u64, n: usize, parts: c_int, first: *mut usize) -> c_int;
+    pub fn qoa_b200_mctx_partition(mctx: *const qoa_b200_mctx, weight: *const u64, n: usize, first: *mut usize) -> c_int;
+    pub fn qoa_b200_mctx_encode_all_batch(mctx: *mut qoa_b200_mctx, descs: *const qoa_b200_desc, pcm: *const *const i16,
+        pcm_len: *const usize, out: *const *mut u8, out_cap: *const usize, out_len: *mut usize, status: *mut i32,
+        n: usize) -> c_int;
+    pub fn qoa_b200_mctx_decode_all_batch(mctx: *mut qoa_b200_mctx, qoa: *const *const u8, len: *const usize, n: usize,
+        mode: c_int, out: *const *mut i16, out_cap: *const usize, info: *mut qoa_b200_stream_info,
+        status: *mut i32) -> c_int;
 }

@@ -606,3 +606,44 @@ def test_encode_all_batch_pipelined(eng, N):
         assert outs[i].size == size and np.array_equal(outs[i], ref[i]), i
     for j, d in enumerate(extra):
         assert outs[n_streams + j].tobytes() == ob.encode_all(pcm_list[n_streams + j], *d)[1], d
+
+
+def test_multi_device_context(eng, N):
+    """qoa_b200_ctx_create_multi: one process, several GPUs, batches sharded by stream (contiguous, balanced by work),
+    results in caller order and identical to the single-device path and to the oracle.  With one visible GPU the same
+    device is listed twice: two contexts, two host threads, same sharding logic."""
+    import torch
+    import qoaudio_b200 as q
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0]
+    m = q.MultiEngine(devices)
+    assert m.devices == devices
+    shapes = [(1 + i % 8, [8000, 44100, 48000][i % 3], n) for i, n in
+              enumerate([1, 19, 5120, 5121, 30000, 777, 12345, 20, 65000, 2 * 5120 + 3, 40000, 9])]
+    pcm = [signals.synth_pcm(61, i, c, n, "noise" if i % 4 == 3 else "music") for i, (c, r, n) in enumerate(shapes)]
+    shapes.insert(5, (0, 44100, 10))       # a failing stream in the middle of a shard
+    pcm.insert(5, np.zeros(10, np.int16))
+    st, enc = m.encode_all_batch(pcm, shapes)
+    st1, enc1 = eng.encode_all_batch(pcm, shapes)
+    assert st == st1 and st[5] == N.ENC_INVALID_CHANNELS
+    for i, (p, s) in enumerate(zip(pcm, shapes)):
+        if st[i] == 0:
+            assert enc[i].tobytes() == enc1[i].tobytes() == ob.encode_all(p, *s)[1], s
+    streams = [e for i, e in enumerate(enc) if st[i] == 0] + [np.frombuffer(b"nope" + bytes(60), dtype=np.uint8)]
+    caps = [s[0] * s[2] for i, s in enumerate(shapes) if st[i] == 0] + [16]
+    info, dst, outs = m.decode_all_batch(streams, caps)
+    info1, dst1, outs1 = eng.decode_all_batch(streams, caps)
+    assert (dst == dst1).all() and dst[-1] == N.DEC_NOT_QOA_FILE and (info == info1).all()
+    for i, s in enumerate(streams[:-1]):
+        assert np.array_equal(outs[i], outs1[i]) and np.array_equal(outs[i], ob.decode_all(s.tobytes())[1]), i
+    # the split is the documented one: contiguous, balanced by encoded length
+    parts = m.partition([len(s) for s in streams])
+    assert parts[0][0] == 0 and parts[-1][1] == len(streams) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+    assert m.kernel_launches() > 0
+    # big enough to take the pipelined host path on every device
+    big = [np.frombuffer(ob.encode_all(signals.synth_pcm(62, i, 2, 5120 * 40), 2, 44100, 5120 * 40)[1], dtype=np.uint8)
+           for i in range(4)] * 48
+    info, dst, outs = m.decode_all_batch(big, [2 * 5120 * 40] * len(big))
+    ref = [ob.decode_all(b.tobytes())[1] for b in big[:4]]
+    assert (dst == 0).all() and all(np.array_equal(o, ref[i % 4]) for i, o in enumerate(outs))
+    m.close()

@@ -87,3 +87,21 @@ def test_world_size_2_gloo(tmp_path):
     for i, s in enumerate(shapes):
         want = ob.encode_all(signals.synth_pcm(1, i, s[0], s[2]), *s)[1].hex()
         assert res["sha"][str(i)] == want
+
+
+def test_partition_is_the_c_abi_one():
+    """shard.partition_contiguous is qoa_b200_partition (host arithmetic of the C ABI, no GPU needed): the split a
+    multi-device context uses inside one process is the split torchrun ranks use."""
+    import ctypes as C
+    from qoaudio_b200 import _native as N, partition
+    from qoaudio_b200.shard import partition_contiguous
+    w = np.array([7, 1, 1, 1, 9, 2, 2, 5], dtype=np.uint64)
+    first = (C.c_size_t * 4)()
+    assert N.lib().qoa_b200_partition(C.c_void_p(w.ctypes.data), w.size, 3, first) == 0
+    assert list(first) == [0, 3, 5, 8] and partition(w, 3) == [(0, 3), (3, 5), (5, 8)] == partition_contiguous(w.tolist(), 3)
+    assert N.lib().qoa_b200_partition(C.c_void_p(w.ctypes.data), w.size, 0, first) == N.E_ARG
+    # without a device the multi-device context fails loudly (no CPU fallback), it does not degrade to something else
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert N.lib().qoa_b200_ctx_create_multi(None, 0, C.byref(h)) != 0 and not h
