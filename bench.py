@@ -610,8 +610,7 @@ def main():
         "dtype": "i32", "data": "synthetic", "config": workload_config(args),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
-                     "kernel": ("decode_fast_kernel<CH=2,S=3,NB=1,512,two codes per lookup>" if S * 517 >= 512 * 148 * 8
-                                else "decode_fast_kernel<CH=2,S=3,NB=1,256>"), "kernel_ms": kern_ms,
+                     "kernel": "decode_fast_kernel<CH=2,S=3,NB=1,256> (uniform-warp loop + general loop)", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "peak_kind": "MEASURED_PEAKS.json hbm_gbs (of measured)" if PEAKS.get("hbm_gbs") else "of fallback",
                      "note": "the kernel is bound by integer issue (16 IMAD + 12 ALU per stereo sample pair on two "

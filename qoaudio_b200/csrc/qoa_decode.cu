@@ -317,6 +317,11 @@ cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_
 // delta of update(), src/lib.rs:822) and is replicated 16 times so that the 16 lanes of a half-warp (one wavefront of
 // a 64-bit shared load) read 16 distinct bank pairs: copy (L & 15) of entry e lives at byte e*128 + (L & 15)*8
 // (16 KiB, conflict-free).
+// (Round 1 also had a 64 KiB table indexed by two codes at once - one LDS.128 per two samples, 8.5 % fewer instructions,
+// but two-way bank conflicts on almost every load: 499 M conflicts per 1280 streams, L1TEX 90 %, +2 % net.  With the
+// uniform-warp loop of round 2 this conflict-free table is as fast at 98 M conflicts and a quarter of the shared
+// memory, so the two-code path is gone; an 8-copy conflict-free version of it only fits next to 80-byte staging rows
+// and is then bound by the TMA engine's row rate, 36.0 ms against 27.2 ms: profiles/r02_decode_experiments.md.)
 constexpr int kLutBytes = 128 * 16 * 8;
 constexpr uint32_t kLutAlign = 1024; // bits 7..9 of the base must be zero: code offsets are OR-ed into the address
 
@@ -448,85 +453,6 @@ __device__ __forceinline__ uint32_t decode_pair_step(Chain &a, Chain &b, uint32_
     const int2 tb = lds_v2(row_b | code_off<I>(wb.x, wb.y));
     return pair_core(a, b, ta, tb);
 }
-
-// ---- two codes per lookup (stereo fast path) -------------------------------------------------------------------------
-// Entry (sf, c1, c2) = {dq(c1), dq(c1) >> 4, dq(c2), dq(c2) >> 4}, 16 bytes, four copies (lane & 3): byte
-// sf * 4096 + (c1 * 8 + c2) * 64 + (lane & 3) * 16, 64 KiB.  One SHF + LOP3 + LDS.128 serves two samples instead of two
-// SHF + LOP3 + LDS.64; the price is one CTA per SM and two-way bank conflicts on almost every load (lanes l and l + 4 of
-// a quarter-warp share a copy).  Eight copies (128 KiB, conflict-free: 58 M conflicts instead of 499 M) only fit next to
-// one-slice (80-byte) staging rows, and those are bound by the TMA engine's row rate (~10 cycles per box row per SM):
-// 36.0 ms against 27.2 ms for the headline batch (round 2, profiles/r02_decode_two_code_8_copies_ncu.txt).
-constexpr int kLut2Bytes = 16 * 64 * 4 * 16;
-constexpr uint32_t kLut2Align = 4096; // bits 6..11 of the base must be zero
-
-__device__ __forceinline__ void fill_lut2(uint8_t *lut)
-{
-    int4 *v = reinterpret_cast<int4 *>(lut);
-    for (int i = threadIdx.x; i < 16 * 64 * 4; i += blockDim.x) {
-        const int sf = i >> 8, c1 = (i >> 5) & 7, c2 = (i >> 2) & 7;
-        const int d1 = c_dequant[sf * 8 + c1], d2 = c_dequant[sf * 8 + c2];
-        v[i] = make_int4(d1, d1 >> 4, d2, d2 >> 4);
-    }
-    __syncthreads();
-}
-
-// Byte offset ((c1 * 8 + c2) * 64) of the codes of samples I and I + 1 (I even).
-template <int I>
-__device__ __forceinline__ uint32_t code2_off(uint32_t hi, uint32_t lo)
-{
-    constexpr int pos = 54 - 3 * I; // LSB of the second code within the 64-bit word
-    constexpr int sh = pos - 6;     // shift that brings the six bits to bits 11..6
-    uint32_t v;
-    if constexpr (sh >= 32)
-        v = hi >> (sh - 32);
-    else if constexpr (sh > 0)
-        v = __funnelshift_r(lo, hi, sh);
-    else if constexpr (sh == 0)
-        v = lo;
-    else
-        v = lo << (-sh);
-    return v & 0xfc0u;
-}
-
-__device__ __forceinline__ int4 lds_v4(uint32_t addr)
-{
-    int4 v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-
-template <int I>
-struct PairLoop2 {
-    static __device__ __forceinline__ void run(Chain &a, Chain &b, uint32_t row_a, uint32_t row_b, uint2 wa, uint2 wb,
-                                               uint32_t *o)
-    {
-        const int4 ta = lds_v4(row_a | code2_off<I>(wa.x, wa.y));
-        const int4 tb = lds_v4(row_b | code2_off<I>(wb.x, wb.y));
-        o[I] = pair_core(a, b, make_int2(ta.x, ta.y), make_int2(tb.x, tb.y));
-        o[I + 1] = pair_core(a, b, make_int2(ta.z, ta.w), make_int2(tb.z, tb.w));
-        PairLoop2<I + 2>::run(a, b, row_a, row_b, wa, wb, o);
-    }
-};
-template <>
-struct PairLoop2<20> {
-    static __device__ __forceinline__ void run(Chain &, Chain &, uint32_t, uint32_t, uint2, uint2, uint32_t *) {}
-};
-
-__device__ __forceinline__ uint32_t two_core(Chain &c, int2 t0, int2 t);
-
-template <int I>
-struct SingleLoop2 { // mono: the two codes of one lookup are two consecutive samples = one output word
-    static __device__ __forceinline__ void run(Chain &a, uint32_t row_a, uint2 wa, uint32_t *o)
-    {
-        const int4 t = lds_v4(row_a | code2_off<I>(wa.x, wa.y));
-        o[I / 2] = two_core(a, make_int2(t.x, t.y), make_int2(t.z, t.w));
-        SingleLoop2<I + 2>::run(a, row_a, wa, o);
-    }
-};
-template <>
-struct SingleLoop2<20> {
-    static __device__ __forceinline__ void run(Chain &, uint32_t, uint2, uint32_t *) {}
-};
 
 template <int I>
 struct PairLoop {
@@ -665,11 +591,12 @@ __device__ __forceinline__ void sts64(uint32_t saddr, uint32_t a, uint32_t b)
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
 }
 
-template <int CH, int S, int NB, int THREADS, bool P2 = false>
+template <int CH, int S, int NB, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 5 : THREADS <= 192 ? 3 : THREADS <= 352 ? 2 : 1))
 decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
                    const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap out_map_rem,
+                   const __grid_constant__ CUtensorMap out_map32, const __grid_constant__ CUtensorMap out_map32_rem,
                    int use_map)
 {
     using Cfg = FastCfg<CH, S, NB>;
@@ -677,15 +604,10 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kRowWords = Cfg::kOutRowBytes / 4;
     constexpr uint32_t kSliceWords = Cfg::kSliceBytes / 4;
-    constexpr int kLutBytes = P2 ? kLut2Bytes : qoa::kLutBytes;       // shadows the single-code constants below
-    constexpr uint32_t kLutAlign = P2 ? kLut2Align : qoa::kLutAlign;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
-    if (P2)
-        fill_lut2(smem);
-    else
-        fill_lut(smem);
+    fill_lut(smem);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t fi = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
 
@@ -749,7 +671,7 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
         if (CH == 2) load_lms(b, fp + 24);
     }
     uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
-    const uint32_t lane_row = smem_u32(smem) + (P2 ? (lane & 3) * 16 : (lane & 15) * 8);
+    const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
     const uint32_t warp_tiles = smem_u32(smem + kLutBytes) + (threadIdx.x >> 5) * Cfg::kWarpBytes;
     // per-warp table {PCM pointer, nsamp} of the 32 rows for the row-by-row copy path
     const uint32_t rows_meta = smem_u32(smem + kLutBytes) + (THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes) +
@@ -760,6 +682,90 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
                      "r"((uint32_t)(p64 >> 32)), "r"(nsamp), "r"(0u)
                      : "memory");
         __syncwarp();
+    }
+
+    // One slice of this lane's frame: read its words out of the input ring, decode 20 samples per channel, stage the
+    // PCM at dst_s.  (Both loops below inline it.)
+    auto fetch_ahead = [&](uint32_t k) {
+        if (CH == 2) {
+            fetch(k + 3);
+            cp_async_commit();
+            cp_async_wait<2>(); // vectors k and k + 1 have landed (only k + 2 and k + 3 may still be in flight)
+        } else {
+            if ((k & 1) == 0) fetch(k / 2 + 2);
+            cp_async_commit();
+            cp_async_wait<2>(); // everything fetched up to two slices ago has landed: vectors <= (k + 1) / 2
+        }
+    };
+    auto slice_body = [&](uint32_t k, uint32_t dst_s) {
+        if (CH == 2) {
+            // slice k = bytes [skew + 16k, skew + 16k + 16) of the vector stream: no alignment selects needed
+            const uint2 ra = lds64(in_ring + (k & 3) * 512 + skew);
+            const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
+            const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
+            const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
+            uint32_t o[20];
+            PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        } else {
+            // slice k = bytes [skew + 8k, skew + 8k + 8) of the vector stream
+            const uint32_t byte = skew + 8 * k;
+            const uint2 ra = lds64(in_ring + ((byte >> 4) & 3) * 512 + (byte & 8));
+            const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+            uint32_t o[10];
+            SingleLoop<0>::run(a, row_a, wa, o);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) sts64(dst_s + i * 8, o[2 * i], o[2 * i + 1]); // 40 bytes per slice: rows stay 8-byte aligned
+        }
+    };
+
+    // ---- uniform warps: 32 full frames that are neighbours in one stream (94 % of the warps of a 60 s batch) ------
+    // Nothing is data dependent here: every lane runs 256 slices, every group of S slices leaves as ONE 32-row tensor
+    // store issued by lane 0, and none of the bookkeeping of the general loop below (per-lane slice counts, per-box
+    // regularity, the row-by-row copy path) is needed: ~35 instructions per slice less.
+    if (NB == 1 && use_map == 2) {
+        const uint64_t out00 = __shfl_sync(kFull, out_byte, 0);
+        if (__all_sync(kFull, nsamp == (uint32_t)kFrameLen && out_byte == out00 + (uint64_t)lane * Cfg::kOutRowBytes)) {
+            constexpr uint32_t kMain = kSlicesPerFrame - kRem; // slices that leave in full groups
+            const uint32_t tile = warp_tiles;
+            int c1 = (int)(out00 / Cfg::kOutRowBytes), c0 = (int)((out00 % Cfg::kOutRowBytes) / 4);
+            uint32_t dst = tile + lane * Cfg::kRowBytes, j = 0;
+#pragma unroll 1
+            for (uint32_t k = 0; k < (uint32_t)kSlicesPerFrame; ++k) {
+                if (j == 0) { // the tensor store that last read this tile has drained it (moving this wait behind the
+                    bulk_wait_read<0>(); // slice's arithmetic was measured: no gain, the other warps hide it)
+                    __syncwarp();
+                }
+                fetch_ahead(k);
+                slice_body(k, dst);
+                dst += Cfg::kSliceBytes;
+                if (++j == S) {
+                    fence_async_smem(); // staging stores -> visible to the async proxy
+                    __syncwarp();
+                    if (lane == 0) tensor_store_2d(&out_map32, tile, c0, c1);
+                    bulk_commit();
+                    c0 += S * kSliceWords;
+                    if (c0 >= (int)kRowWords) {
+                        c0 -= (int)kRowWords;
+                        c1 += 1;
+                    }
+                    j = 0; // the last, shorter group of the frame is staged densely (pitch = its box width)
+                    dst = tile + lane * (k + 1 == kMain ? kRem * Cfg::kSliceBytes : (uint32_t)Cfg::kRowBytes);
+                }
+            }
+            if (kRem) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tensor_store_2d(&out_map32_rem, tile, c0, c1);
+                bulk_commit();
+            }
+            bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read the tile
+            return;
+        }
     }
 
     uint32_t ring = 0;   // tile of the ring being filled
@@ -776,47 +782,8 @@ decode_fast_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict
             pitch = min((uint32_t)S, nsl_max - k) * Cfg::kSliceBytes; // TMA reads the tile densely: pitch = box width
         }
         const uint32_t row = tile + lane * pitch;
-        if (CH == 2) {
-            fetch(k + 3);
-            cp_async_commit();
-            cp_async_wait<2>(); // vectors k and k + 1 have landed (only k + 2 and k + 3 may still be in flight)
-        } else {
-            if ((k & 1) == 0) fetch(k / 2 + 2);
-            cp_async_commit();
-            cp_async_wait<2>(); // everything fetched up to two slices ago has landed: vectors <= (k + 1) / 2
-        }
-        if (k < nslices) {
-            const uint32_t dst_s = row + in_row * Cfg::kSliceBytes;
-            if (CH == 2) {
-                // slice k = bytes [skew + 16k, skew + 16k + 16) of the vector stream: no alignment selects needed
-                const uint2 ra = lds64(in_ring + (k & 3) * 512 + skew);
-                const uint2 rb = lds64(in_ring + ((k + (skew >> 3)) & 3) * 512 + (8 - skew));
-                const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
-                const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
-                const uint32_t row_a = lane_row + (wa.x >> 28) * (P2 ? 4096 : 1024); // sf = top nibble (:303)
-                const uint32_t row_b = lane_row + (wb.x >> 28) * (P2 ? 4096 : 1024);
-                uint32_t o[20];
-                if (P2)
-                    PairLoop2<0>::run(a, b, row_a, row_b, wa, wb, o);
-                else
-                    PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) sts128(dst_s + i * 16, o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-            } else {
-                // slice k = bytes [skew + 8k, skew + 8k + 8) of the vector stream
-                const uint32_t byte = skew + 8 * k;
-                const uint2 ra = lds64(in_ring + ((byte >> 4) & 3) * 512 + (byte & 8));
-                const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
-                const uint32_t row_a = lane_row + (wa.x >> 28) * (P2 ? 4096 : 1024);
-                uint32_t o[10];
-                if (P2)
-                    SingleLoop2<0>::run(a, row_a, wa, o);
-                else
-                    SingleLoop<0>::run(a, row_a, wa, o);
-#pragma unroll
-                for (int i = 0; i < 5; ++i) sts64(dst_s + i * 8, o[2 * i], o[2 * i + 1]); // 40 bytes per slice: rows stay 8-byte aligned
-            }
-        }
+        fetch_ahead(k);
+        if (k < nslices) slice_body(k, row + in_row * Cfg::kSliceBytes);
         ++in_row;
         if (in_row == S || k + 1 == nsl_max) {
             fence_async_smem(); // staging stores -> visible to the async proxy
@@ -1103,54 +1070,6 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
     }
 }
 
-__global__ void smem_base_probe(uint32_t *out)
-{
-    extern __shared__ uint8_t probe_smem[];
-    *out = smem_u32(probe_smem);
-}
-
-// Bytes between the start of dynamic shared memory (of a kernel without static shared memory) and the next 4 KiB
-// boundary of the shared window, measured once per device; -1 if it cannot be measured.
-static int p2_pad()
-{
-    static int pad[64];
-    static bool done[64] = {false};
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-    if (!done[dev]) {
-        uint32_t *d = nullptr, h = 0;
-        pad[dev] = -1;
-        if (cudaMalloc(&d, sizeof h) == cudaSuccess) {
-            smem_base_probe<<<1, 1, 16>>>(d);
-            if (cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess)
-                pad[dev] = (int)((kLut2Align - (h & (kLut2Align - 1))) & (kLut2Align - 1));
-            cudaFree(d);
-        }
-        cudaGetLastError();
-        done[dev] = true;
-    }
-    return pad[dev];
-}
-
-// The two-code kernel runs one 512-thread CTA per SM: worth it only when the grid is many waves deep, and possible only
-// if table + tiles fit the device's opt-in shared-memory limit with the measured pad.
-constexpr uint64_t kP2MinFrames = 512ull * 148 * 8;
-static bool p2_usable()
-{
-    static const bool off = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 0; // development aid
-    if (off) return false;
-    const int pad = p2_pad();
-    if (pad < 0) return false;
-    int dev = 0, limit = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
-        return false;
-    using Cfg = FastCfg<2, 3, 1>;
-    return (size_t)pad + kLut2Bytes + 16 * (size_t)(Cfg::kWarpBytes + Cfg::kInWarpBytes + 512) <= (size_t)limit;
-}
-
 // cudaFuncSetAttribute is per device: remember which devices have been configured for each kernel instantiation.
 struct PerDeviceOnce {
     std::atomic<bool> done[64];
@@ -1164,36 +1083,42 @@ struct PerDeviceOnce {
     }
 };
 
-template <int CH, int S, int NB, int THREADS, bool P2 = false>
+template <int CH, int S, int NB, int THREADS>
 static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
                                const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
 {
     using Cfg = FastCfg<CH, S, NB>;
-    // The two-code table needs a 4 KiB-aligned base: the pad is computed from the measured start of dynamic shared
-    // memory (p2_pad()), because 512 threads + 64 KiB only fit the 227 KiB limit with the exact pad (3072 bytes today).
-    const size_t smem = (P2 ? (size_t)p2_pad() + kLut2Bytes : kLutAlign + kLutBytes) +
+    const size_t smem = kLutAlign + kLutBytes +
                         (size_t)(THREADS / 32) * (Cfg::kWarpBytes + Cfg::kInWarpBytes + 512);
     static PerDeviceOnce configured;
     std::atomic<bool> *cfg = configured.slot();
     if (!cfg || !cfg->load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS, P2>,
+        cudaError_t e = cudaFuncSetAttribute(decode_fast_kernel<CH, S, NB, THREADS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (cfg) cfg->store(true, std::memory_order_release);
     }
-    CUtensorMap map, map_rem;
+    CUtensorMap map, map_rem, map32, map32_rem;
     memset(&map, 0, sizeof map);
     memset(&map_rem, 0, sizeof map_rem);
+    memset(&map32, 0, sizeof map32);
+    memset(&map32_rem, 0, sizeof map32_rem);
     constexpr uint32_t kRem = kSlicesPerFrame % S;
     int use_map = make_out_map(&map, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes, Cfg::kBoxRows);
     if (use_map && kRem) // the last group of a full frame holds 256 % S slices: same tile pitch, narrower box
         use_map = std::min(use_map, make_out_map(&map_rem, d_out, out_bytes, kRem * Cfg::kSliceBytes / 4, Cfg::kOutRowBytes,
                                                  Cfg::kBoxRows));
+    if (use_map == 2) { // the same views with 32-row boxes: warps whose 32 frames are neighbours in one stream
+        int wide = make_out_map(&map32, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes, 32);
+        if (wide == 2 && kRem)
+            wide = make_out_map(&map32_rem, d_out, out_bytes, kRem * Cfg::kSliceBytes / 4, Cfg::kOutRowBytes, 32);
+        if (wide != 2) use_map = 1; // the uniform-warp loop needs use_map == 2
+    }
     if (const char *dbg = getenv("QOA_B200_TMAP")) use_map = std::min(use_map, atoi(dbg)); // development aid: 0 = no tensor stores, 1 = no overlapping rows
     const uint64_t blocks = (n_frames + THREADS - 1) / THREADS;
     if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    decode_fast_kernel<CH, S, NB, THREADS, P2><<<(unsigned)blocks, THREADS, smem, s>>>(d_arena, d_recs, n_frames,
-                                                                                       d_out_base, d_out, map, map_rem, use_map);
+    decode_fast_kernel<CH, S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(
+        d_arena, d_recs, n_frames, d_out_base, d_out, map, map_rem, map32, map32_rem, use_map);
     return cudaGetLastError();
 }
 
@@ -1204,20 +1129,10 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
     if (n_frames == 0 || max_ch == 0) return cudaSuccess;
     cudaError_t e;
     if (uniform_ch == 2) {
-        // 256 threads x 2 CTAs per SM is the measured best (128 / 192 / 288 / 320 / 640 threads: DESIGN.md section 4)
-        // big batches: two codes per lookup, one 512-thread CTA per SM (+2-2.5 %); otherwise 256 threads x 2 CTAs per SM,
-        // the measured best of 128 / 192 / 256 / 288 / 320 / 640 threads
-        static const bool force_p2 = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 2; // development aid
-        if ((n_frames >= kP2MinFrames || force_p2) && p2_usable())
-            e = launch_fast<2, 3, 1, 512, true>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
-        else
-            e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        // 256 threads x 2 CTAs per SM: the measured best of 128 / 192 / 256 / 288 / 320 / 512 / 640 threads
+        e = launch_fast<2, 3, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch == 1) {
-        static const bool force_p2 = getenv("QOA_B200_DEC_P2") && atoi(getenv("QOA_B200_DEC_P2")) == 2; // development aid
-        if ((n_frames >= kP2MinFrames || force_p2) && p2_usable())
-            e = launch_fast<1, 6, 1, 512, true>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
-        else
-            e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
+        e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch >= 3 && uniform_ch <= 8) {
         const size_t smem = kLutAlign + kLutBytes + (size_t)(kMultiThreads / 32) * (kMultiTileBytes + 2048 + 512);
         {

@@ -517,11 +517,13 @@ def test_batch_tensor_rows_move_as_strided_copies(eng):
     assert (dec[:, n * ch:] == 77).all()                                      # nothing written past a row's samples
 
 
-@pytest.mark.parametrize("p2", ["0", "2"])
-def test_stereo_decode_kernel_variants(p2):
-    """Big stereo and mono batches decode with two codes per table lookup (one 512-thread CTA per SM), smaller ones with one code
-    per lookup.  Both kernels are forced in turn (QOA_B200_DEC_P2 is read once per process, hence the subprocess) on
-    full frames, partial frames and slices, stream boundaries inside a warp and truncated streams."""
+@pytest.mark.parametrize("tmap", ["2", "1", "0"])
+def test_stereo_decode_kernel_variants(tmap):
+    """The mono / stereo kernel has two loops: warps whose 32 frames are full-size neighbours in one stream take the
+    stripped uniform loop (one 32-row tensor store per group), every other warp the general loop (8-row boxes, row
+    copies for irregular boxes).  QOA_B200_TMAP caps the tensor-map mode (read per launch; a subprocess keeps the
+    environment clean): 2 = both loops, 1 = general loop only, 0 = no tensor stores at all.  All three must agree with
+    the oracle on full frames, partial frames and slices, stream boundaries inside a warp and truncated streams."""
     import subprocess
     import sys
     code = """
@@ -532,8 +534,10 @@ from oracle import binding as ob
 eng = qoaudio_b200.default_engine()
 lens = [5120, 5120 * 3, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 4080, 2 * 5120 + 3082, 5120 * 40 + 119]
 enc = [ob.encode_all(signals.synth_pcm(51, i, 2, n, 'noise' if i % 3 == 1 else 'music'), 2, 44100, n)[1] for i, n in enumerate(lens)]
-streams = enc * 5 + [e[:len(e) - 11] for e in enc[:4]] + [open({root!r} + '/tests/golden/julien_baker_sprained_ankle.qoa', 'rb').read()]
+long_ = [ob.encode_all(signals.synth_pcm(53, i, 2, 5120 * 70 + 333 * i), 2, 44100, 5120 * 70 + 333 * i)[1] for i in range(3)]  # 70 full frames: whole warps are uniform
+streams = enc * 5 + long_ + [e[:len(e) - 11] for e in enc[:4]] + [open({root!r} + '/tests/golden/julien_baker_sprained_ankle.qoa', 'rb').read()]
 mono = [ob.encode_all(signals.synth_pcm(52, i, 1, n + 1, 'noise' if i % 4 == 2 else 'music'), 1, 16000, n + 1)[1] for i, n in enumerate(lens)]
+mono += [ob.encode_all(signals.synth_pcm(54, 0, 1, 5120 * 40 + 7), 1, 8000, 5120 * 40 + 7)[1]]
 for batch in (streams, mono * 4 + [e[:len(e) - 9] for e in mono[:3]]):   # all-stereo, then all-mono: each takes its own kernel
     for mode in (0, 1):
         infos, outs = eng.decode_batch(batch, mode)
@@ -544,7 +548,7 @@ for batch in (streams, mono * 4 + [e[:len(e) - 9] for e in mono[:3]]):   # all-s
 print('variants ok')
 """
     from conftest import ROOT
-    env = dict(os.environ, QOA_B200_DEC_P2=p2)
+    env = dict(os.environ, QOA_B200_TMAP=tmap)
     r = subprocess.run([sys.executable, "-c", code.format(root=ROOT)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "variants ok" in r.stdout, r.stdout + r.stderr
 

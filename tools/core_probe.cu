@@ -2,7 +2,8 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I qoaudio_b200/csrc -o tools/core_probe tools/core_probe.cu -lcuda
 // Kinds: 0 = pair_core only (tables replaced by kernel arguments): 16 IMAD + 9 ALU per sample pair
 //        1 = + single-code lookups from the shared-memory table (SHF + LOP3 + LDS.64 per sample and channel)
-//        2 = + two-code lookups (4 copies); 4..7 = pieces of the lookup in isolation (see ProbeLoop)
+//        4..7 = pieces of the lookup in isolation (see ProbeLoop).  (Round 2 also measured the since-removed two-code
+//        table here: 22.4 ms, profiles/r02_decode_experiments.md.)
 // Each thread decodes `slices` pseudo slices (the slice words come from a counter hash, no global loads), 20 steps each,
 // and folds the output words into a checksum.  Reported: ns per sample pair per SM-scheduler and the implied time of the
 // headline batch (8192 x 60 s stereo = 21.68 G sample pairs) on 148 SMs.
@@ -50,16 +51,15 @@ template <int KIND, int THREADS, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS) core_kernel(uint32_t *out, int slices, int2 ka, int2 kb)
 {
     extern __shared__ uint8_t smem_raw[];
-    constexpr uint32_t align = KIND == 2 ? kLut2Align : kLutAlign;
+    constexpr uint32_t align = kLutAlign;
     uint8_t *smem = smem_raw + ((align - (smem_u32(smem_raw) & (align - 1))) & (align - 1));
     if (KIND == 1 || KIND >= 4) fill_lut(smem);
-    if (KIND == 2) fill_lut2(smem);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t tid = blockIdx.x * THREADS + threadIdx.x;
     Chain a{(int)tid, 3, -5, 7, 100, -200, -8192, 16384, 1, 1, -1, 1}, b = a;
     b.h0 = 11;
     uint32_t sum = 0;
-    uint32_t lane_row = smem_u32(smem) + (KIND == 2 ? (lane & 3) * 16 : (lane & 15) * 8);
+    uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
     uint2 wa = make_uint2(tid * 2654435761u, tid * 40503u + 17), wb = make_uint2(~wa.x, wa.y ^ 0x5bd1e995u);
 #pragma unroll 1
     for (int k = 0; k < slices; ++k) {
@@ -68,14 +68,13 @@ __global__ void __launch_bounds__(THREADS, CTAS) core_kernel(uint32_t *out, int 
 #pragma unroll
             for (int i = 0; i < 20; ++i) o[i] = pair_core(a, b, ka, kb);
         } else {
-            const uint32_t row_a = lane_row + (wa.x >> 28) * (KIND == 2 ? 4096 : 1024);
-            const uint32_t row_b = lane_row + (wb.x >> 28) * (KIND == 2 ? 4096 : 1024);
+            const uint32_t row_a = lane_row + (wa.x >> 28) * 1024;
+            const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
             if (KIND == 1) PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
             if (KIND == 4) ProbeLoop<0, 4>::run(a, b, row_a, row_b, wa, wb, o, ka, kb);
             if (KIND == 5) ProbeLoop<0, 5>::run(a, b, row_a, row_b, wa, wb, o, ka, kb);
             if (KIND == 6) ProbeLoop<0, 6>::run(a, b, row_a, row_b, wa, wb, o, ka, kb);
             if (KIND == 7) ProbeLoop<0, 7>::run(a, b, row_a, row_b, wa, wb, o, ka, kb);
-            if (KIND == 2) PairLoop2<0>::run(a, b, row_a, row_b, wa, wb, o);
             wa.x = wa.x * 1664525u + 1013904223u; wa.y ^= wa.x >> 3;   // next pseudo slice words
             wb.x = wb.x * 22695477u + 1u; wb.y ^= wb.x >> 5;
         }
@@ -89,7 +88,7 @@ template <int KIND, int THREADS, int CTAS>
 static void run(int sms, uint32_t *d_out, const char *name)
 {
     const int slices = 4096;
-    const size_t smem = (KIND == 2 ? 4096 + kLut2Bytes : KIND >= 1 ? 1024 + kLutBytes : 0) +
+    const size_t smem = (KIND >= 1 ? 1024 + kLutBytes : 0) +
                         (CTAS >= 2 ? 60000 : 120000); // plus a tile footprint, so that exactly CTAS CTAs fit on an SM
     cudaFuncSetAttribute(core_kernel<KIND, THREADS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t t0, t1;
@@ -121,6 +120,5 @@ int main()
     run<6, 256, 2>(sms, d, "+ loads only (2 LDS.64, fixed address)");
     run<7, 256, 2>(sms, d, "+ 4 ALU + 2 LDS.32 (dq only)");
     run<4, 256, 2>(sms, d, "+ 4 ALU + 2 LDS.32 + 2 SHF (delta = dq >> 4)");
-    run<2, 512, 1>(sms, d, "+ two-code lookups (4 copies)");
     return 0;
 }

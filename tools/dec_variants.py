@@ -1,6 +1,6 @@
 """Stereo/mono decode kernel variants: parity against the oracle on adversarial streams, then device-resident timing of
-the headline shape.  The variant is chosen by the environment (QOA_B200_DEC_HD / QOA_B200_DEC_P2 are read once per
-process), so run this once per variant:  QOA_B200_DEC_HD=512 python tools/dec_variants.py [streams] [steps] [ch]"""
+the headline shape.  Variants are chosen by the environment (QOA_B200_TMAP = 2 / 1 / 0: both loops / general loop only /
+no tensor stores), so run this once per variant:  QOA_B200_TMAP=1 python tools/dec_variants.py [streams] [steps] [ch]"""
 import os, sys, time, statistics, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -14,7 +14,7 @@ CH = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 RATE, N = 44100, 2646000
 eng = q.Engine(0)
 stream = torch.cuda.current_stream().cuda_stream
-tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("QOA_B200_DEC")) or "default"
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("QOA_B200_")) or "default"
 
 def enc_size(ch, n):
     return 8 + ((n + 5119) // 5120) * (8 + 16 * ch) + ((n + 19) // 20) * 8 * ch
