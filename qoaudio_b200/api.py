@@ -301,7 +301,16 @@ class QoaDecoder:
     # streaming ----------------------------------------------------------------------------------------------
     def decode_frame(self, frame_data):
         """src/lib.rs:641-651: decode one (or more) whole frames given as bytes; returns the samples.
-        As in the reference, after an error the decoder must not be used again."""
+        As in the reference, after an error the decoder must not be used again.
+
+        The reference appends `frame_data` to a persistent Cursor and iterates to EOF.  Because every QOA frame carries
+        its own LMS state (:270-281) and Streaming mode never raises IncompatibleFrame (:255-258), the only state that
+        survives a successful call is the cursor position, which then sits at the end of the buffer: a call whose bytes
+        are whole frames therefore decodes exactly as a stateless call does, which is what this method is.  Bytes that
+        are NOT whole frames behave as in the reference, too: a frame cut after its 8-byte header is IoError
+        (UnexpectedEof, and the reference decoder is unusable afterwards, :666-667), and 1-7 trailing bytes are consumed
+        silently (read_exact on a Cursor moves to the end on a short read - the semantics the oracle restates,
+        oracle/qoa_oracle.c rd()); neither implementation can resume a frame that was split across two calls."""
         if not self._frame_mode:
             raise TypeError("decode_frame is only available on QoaDecoder.new_streaming()")
         infos, outs = self._eng.decode_batch([bytes(frame_data)], N.DECODE_FRAMES)

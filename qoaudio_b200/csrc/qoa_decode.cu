@@ -309,6 +309,19 @@ cudaError_t launch_index_fill_regular(const uint8_t *d_arena, const uint64_t *d_
     return cudaGetLastError();
 }
 
+// cudaFuncSetAttribute is per device: remember which devices have been configured for each kernel instantiation.
+struct PerDeviceOnce {
+    std::atomic<bool> done[64];
+    PerDeviceOnce() { for (auto &d : done) d.store(false); }
+    // returns the slot of the current device, or nullptr when it has to be configured on every launch
+    std::atomic<bool> *slot()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+        return &done[dev];
+    }
+};
+
 // ================================================================================================================
 // Decode
 // ================================================================================================================
@@ -879,42 +892,57 @@ static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint3
 // One thread = one (frame, channel pair): the same two-chain slice loop as stereo (an odd channel count leaves the
 // last pair with one live chain).  The P = ceil(ch / 2) lanes of a frame are neighbours in the warp, 32 / P frames
 // per warp.  Every lane writes its pair's samples into its FRAME's row of a per-warp shared-memory tile
-// ([frames][S slices x 20 samples x ch] interleaved i16, S = 1 for even and 2 for odd channel counts so that a row is a
-// multiple of 16 bytes); after S slices the warp copies the tile out row by row, one half-warp per 256-byte run, so
-// global stores are contiguous runs of the interleaved PCM.  Slice words arrive through a per-lane cp.async ring
-// three slices ahead.  Requirements (host-checked): every frame has `ch` channels and starts 16-byte aligned.
+// ([frames][S slices x 20 samples x ch] interleaved i16; S = 1 for even, 2 for odd channel counts
+// so that a row is a multiple of 16 bytes).  After S slices the tile leaves
+//   * through ONE 2-D tensor store (rows = frames, box = one group of one frame's interleaved PCM) when the warp's
+//     frames are full-size neighbours in one stream - no copy-out instructions (round 1 copied every tile out with
+//     LDS.128 + STG.128: 368 of 1097 instructions per slice for 8 channels);
+//   * otherwise row by row, one half-warp per 256-byte run, so global stores are contiguous runs.
+// The tensor-store path stages densely (the TMA engine reads the box as one dense block), which costs bank conflicts on
+// the per-sample staging stores; the copy path pads the row pitch to an odd multiple of 16 bytes instead.
+// Slice words arrive through a per-lane cp.async ring three slices ahead.  Requirements (host-checked): every frame
+// has CH channels and starts 16-byte aligned.
 constexpr int kMultiThreads = 256;
-constexpr int kMultiTileBytes = 4608; // largest tile: 7 channels = 8 frames x (2 slices x 280 B + 16 B pad)
+constexpr int kMultiTileBytes = 5632; // largest tile: 4 channels = 16 frames x (2 slices x 160 B + 16 B pad) = 5376
+
+template <int CH>
+struct MultiCfg {
+    static constexpr uint32_t P = (CH + 1) / 2;                       // channel pairs per frame
+    static constexpr uint32_t kFpw = 32 / P;                          // frames per warp
+    static constexpr uint32_t S = (CH % 2 == 0) ? 1u : 2u;            // slices per tile row
+    static constexpr uint32_t kSliceBytes = kSliceLen * CH * 2;       // interleaved PCM of one slice of one frame
+    static constexpr uint32_t kRowBytes = S * kSliceBytes;
+    static constexpr uint32_t kPadPitch = kRowBytes + (((kRowBytes >> 4) & 1) ? 0 : 16); // copy path: odd multiple of 16
+    static constexpr uint32_t kOutRowBytes = kFrameLen * CH * 2;      // PCM bytes of one full frame = tensor-map row pitch
+    static_assert(kRowBytes % 16 == 0 && kFpw * kPadPitch <= (uint32_t)kMultiTileBytes, "tile layout");
+    static_assert(kRowBytes / 4 <= 256 && (kSlicesPerFrame % S) == 0, "tensor-map box limits");
+};
 
 __device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
 }
 
+template <int CH>
 __global__ void __launch_bounds__(kMultiThreads, 2)
-decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames, uint32_t ch,
-                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out)
+decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restrict__ recs, uint64_t n_frames,
+                    const uint64_t *__restrict__ out_base, int16_t *__restrict__ out,
+                    const __grid_constant__ CUtensorMap out_map, int use_map)
 {
+    using Cfg = MultiCfg<CH>;
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr int kWarps = kMultiThreads / 32;
+    constexpr uint32_t ch = CH, P = Cfg::P, fpw = Cfg::kFpw, S = Cfg::S, row_bytes = Cfg::kRowBytes;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
     fill_lut(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t P = (ch + 1) / 2;           // channel pairs per frame
-    const uint32_t fpw = 32 / P;               // frames per warp
-    const uint32_t S = (ch & 1) ? 2u : 1u;     // slices per tile row
-    const uint32_t row_bytes = S * kSliceLen * ch * 2;
-    // Row pitch = an odd multiple of 16 bytes: rows start 4 (mod 8) banks apart, so the per-sample staging stores of a
-    // warp (one 32-bit word per lane, lanes = frames x pairs) hit each bank at most twice.  An even multiple lines
-    // every frame's word up on the same banks (6 channels: 240 + 16 = 256 bytes was a 10-way conflict).
-    const uint32_t pitch = row_bytes + (((row_bytes >> 4) & 1) ? 0 : 16);
     const uint32_t fl = lane / P, p = lane - fl * P; // frame within the warp, pair within the frame
     const uint64_t fi = ((uint64_t)blockIdx.x * kWarps + warp) * fpw + fl;
 
     uint32_t nsamp = 0;
-    uint8_t *op = reinterpret_cast<uint8_t *>(out);
+    uint64_t out_byte = 0;
     FrameRec rec;
     rec.in_off = 0;
     if (fl < fpw && fi < n_frames) {
@@ -922,12 +950,20 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
         const uint64_t ob = out_base[rec.stream];
         if (ob != ~0ull) {
             nsamp = rec.nsamp;
-            op += (ob + rec.out_rel) * 2;
+            out_byte = (ob + rec.out_rel) * 2;
         }
     }
+    uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
     const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
     const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
     if (nsl_max == 0) return;
+    // Tensor-store mode (warp-uniform): every frame of the warp is a full frame and frame f sits f rows below frame 0.
+    const uint64_t out00 = __shfl_sync(kFull, out_byte, 0);
+    const bool tma = use_map == 2 &&
+                     __all_sync(kFull, fl >= fpw || (nsamp == (uint32_t)kFrameLen &&
+                                                     out_byte == out00 + (uint64_t)fl * Cfg::kOutRowBytes));
+    const uint32_t pitch = tma ? row_bytes : Cfg::kPadPitch;
+    int map_c1 = (int)(out00 / Cfg::kOutRowBytes), map_c0 = (int)((out00 % Cfg::kOutRowBytes) / 4);
 
     const uint32_t c0 = 2 * p;
     const bool two = c0 + 1 < ch; // the last pair of an odd channel count has one live chain (the other mirrors it)
@@ -971,6 +1007,7 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
     for (uint32_t k = 0; k < nsl_max; ++k) {
         fetch(k + 3);
         cp_async_wait<3>(); // slice k's words have landed
+        uint32_t o[20];
         if (k < nslices) {
             const uint2 ra = lds64(in_ring + (k & 3) * 512);
             const uint2 rb = two ? lds64(in_ring + (k & 3) * 512 + 8) : ra;
@@ -978,9 +1015,14 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
             const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
             const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
             const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
-            uint32_t o[20];
             PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
-            const uint32_t dst = row + in_row * (kSliceLen * ch * 2);
+        }
+        if (tma && in_row == 0) { // the tensor store that last read the tile has drained it: with one-slice groups this
+            bulk_wait_read<0>();  // wait comes every slice, so it sits BEHIND the slice's arithmetic (in front of it the
+            __syncwarp();         // warps spent 2.4 stall cycles per issue on it: profiles/r02_decode_multi_8ch_*.txt)
+        }
+        if (k < nslices) {
+            const uint32_t dst = row + in_row * Cfg::kSliceBytes;
             if (!(ch & 1)) { // even channel counts: the pair is one aligned 32-bit word per sample
 #pragma unroll
                 for (int i = 0; i < 20; ++i) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + i * ch * 2), "r"(o[i]) : "memory");
@@ -994,9 +1036,23 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
         }
         ++in_row;
         if (in_row == S || k + 1 == nsl_max) {
+            if (tma) { // (full frames: in_row == S here)
+                fence_async_smem(); // staging stores -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) tensor_store_2d(&out_map, tile, map_c0, map_c1);
+                bulk_commit();
+                map_c0 += (int)(row_bytes / 4);
+                if (map_c0 >= (int)(Cfg::kOutRowBytes / 4)) {
+                    map_c0 -= (int)(Cfg::kOutRowBytes / 4);
+                    map_c1 += 1;
+                }
+                first += in_row * kSliceLen;
+                in_row = 0;
+                continue;
+            }
             __syncwarp();
             // copy the tile out: one half-warp per 256-byte run of a row
-            const uint32_t runs = (row_bytes + 255) / 256;
+            constexpr uint32_t runs = (row_bytes + 255) / 256;
             for (uint32_t it = lane >> 4; it < fpw * runs; it += 2) {
                 const uint32_t r = it / runs, run = it - r * runs;
                 const uint32_t off = run * 256 + (lane & 15) * 16;
@@ -1025,6 +1081,32 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
         }
     }
     cp_async_wait<0>();
+    bulk_wait_read<0>(); // shared memory must stay valid until the TMA engine has read the tile
+}
+
+template <int CH>
+static cudaError_t launch_multi(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
+                                const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes, cudaStream_t s)
+{
+    using Cfg = MultiCfg<CH>;
+    const size_t smem = kLutAlign + kLutBytes + (size_t)(kMultiThreads / 32) * (kMultiTileBytes + 2048 + 512);
+    static PerDeviceOnce configured;
+    std::atomic<bool> *cfg = configured.slot();
+    if (!cfg || !cfg->load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(decode_multi_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (cfg) cfg->store(true, std::memory_order_release);
+    }
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    int use_map = make_out_map(&map, d_out, out_bytes, Cfg::kRowBytes / 4, Cfg::kOutRowBytes, Cfg::kFpw);
+    if (const char *dbg = getenv("QOA_B200_TMAP")) use_map = std::min(use_map, atoi(dbg)); // development aid
+    const uint64_t warps = (n_frames + Cfg::kFpw - 1) / Cfg::kFpw;
+    const uint64_t blocks = (warps + kMultiThreads / 32 - 1) / (kMultiThreads / 32);
+    if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    decode_multi_kernel<CH><<<(unsigned)blocks, kMultiThreads, smem, s>>>(d_arena, d_recs, n_frames, d_out_base, d_out, map,
+                                                                          use_map);
+    return cudaGetLastError();
 }
 
 // ---- generic path: one thread = one (frame, channel); any channel count (1..255), any alignment ---------------
@@ -1069,19 +1151,6 @@ decode_generic_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restr
             if ((uint32_t)i < emit) op[(uint64_t)(base + i) * ch] = (int16_t)(o[i / 2] >> (16 * (i & 1)));
     }
 }
-
-// cudaFuncSetAttribute is per device: remember which devices have been configured for each kernel instantiation.
-struct PerDeviceOnce {
-    std::atomic<bool> done[64];
-    PerDeviceOnce() { for (auto &d : done) d.store(false); }
-    // returns the slot of the current device, or nullptr when it has to be configured on every launch
-    std::atomic<bool> *slot()
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-        return &done[dev];
-    }
-};
 
 template <int CH, int S, int NB, int THREADS>
 static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames,
@@ -1134,25 +1203,14 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
     } else if (uniform_ch == 1) {
         e = launch_fast<1, 6, 1, 256>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s);
     } else if (uniform_ch >= 3 && uniform_ch <= 8) {
-        const size_t smem = kLutAlign + kLutBytes + (size_t)(kMultiThreads / 32) * (kMultiTileBytes + 2048 + 512);
-        {
-            const uint32_t pairs = (uniform_ch + 1) / 2, rows = 32 / pairs, sl = (uniform_ch & 1) ? 2 : 1;
-            if (rows * (sl * kSliceLen * uniform_ch * 2 + 16) > (uint32_t)kMultiTileBytes) return cudaErrorInvalidValue;
+        switch (uniform_ch) {
+        case 3: e = launch_multi<3>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 4: e = launch_multi<4>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 5: e = launch_multi<5>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 6: e = launch_multi<6>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        case 7: e = launch_multi<7>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
+        default: e = launch_multi<8>(d_arena, d_recs, n_frames, d_out_base, d_out, out_bytes, s); break;
         }
-        static PerDeviceOnce configured;
-        std::atomic<bool> *cfg = configured.slot();
-        if (!cfg || !cfg->load(std::memory_order_acquire)) {
-            e = cudaFuncSetAttribute(decode_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            if (cfg) cfg->store(true, std::memory_order_release);
-        }
-        const uint32_t fpw = 32 / ((uniform_ch + 1) / 2);
-        const uint64_t warps = (n_frames + fpw - 1) / fpw;
-        const uint64_t blocks = (warps + kMultiThreads / 32 - 1) / (kMultiThreads / 32);
-        if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-        decode_multi_kernel<<<(unsigned)blocks, kMultiThreads, smem, s>>>(d_arena, d_recs, n_frames, uniform_ch, d_out_base,
-                                                                          d_out);
-        e = cudaGetLastError();
     } else {
         const uint64_t n_units = n_frames * max_ch;
         const uint64_t blocks = (n_units + kGenThreads - 1) / kGenThreads;

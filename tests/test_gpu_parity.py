@@ -175,8 +175,10 @@ def test_mono_batch_fast_path(eng):
 
 @pytest.mark.parametrize("ch", [3, 4, 5, 6, 7, 8])
 def test_multichannel_batch_fast_path(eng, ch):
-    """Uniform 3..8-channel batches take the pair-per-lane kernel (row tiles + contiguous copy-out)."""
-    lens = [5120, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 1, 4080, 5120 * 3 + 3081, 5120 * 9 + 119]
+    """Uniform 3..8-channel batches take the pair-per-lane kernel: warps whose frames are full-size neighbours in one
+    stream leave through one tensor store per group (the 40-frame stream: 16 frames per warp at most), every other
+    warp through the contiguous row copy."""
+    lens = [5120, 5120 * 2 + 20, 5120 + 1, 5120 + 19, 20, 7, 1, 4080, 5120 * 3 + 3081, 5120 * 9 + 119, 5120 * 40 + 13]
     pcm_list = [signals.synth_pcm(8, i, ch, n, "noise" if i % 4 == 1 else "music") for i, n in enumerate(lens)]
     descs = [(ch, 48000, n) for n in lens]
     st, outs = eng.encode_all_batch(pcm_list, descs)

@@ -1,5 +1,4 @@
 O=gpurun_out
-rm -f $O/dv.txt
-for v in "" "" ; do env $v python tools/dec_variants.py 8192 20 2>&1 | grep "^\[" >> $O/dv.txt; done
-python tools/dec_variants.py 8192 10 1 2>&1 | grep "^\[" >> $O/dv.txt
-cat $O/dv.txt
+python -m pytest tests -x -q -m gpu -k "multichannel" 2>&1 | tail -2
+python tools/decode_shapes.py 4:2048:512000 > $O/shapes.txt 2>&1
+cat $O/shapes.txt
