@@ -436,6 +436,28 @@ def test_mixed_classes_device_offsets(eng):
             assert {k: plan.info[i][k] for k in INFO_KEYS} == oi, i
             assert np.array_equal(host[out_off[i]:out_off[i] + caps[i]], opcm), (i, misalign)
         plan.close()
+    # Base pointers that are not 16-byte aligned (a torch view with a storage offset): the output arena then takes the
+    # generic kernel for every class (the fast kernels store 16-byte rows), a misaligned input arena is refused.
+    caps = [len(x[1]) for x in expect]
+    out_off = np.concatenate([[0], np.cumsum([(c + 7) // 8 * 8 for c in caps])[:-1]]).astype(np.uint64)
+    big = torch.full((int(out_off[-1]) + caps[-1] + 16,), -21846, dtype=torch.int16, device="cuda")
+    view = big[3:]                                   # data_ptr() is 6 bytes past a 256-byte boundary
+    assert view.data_ptr() % 16 == 6
+    plan = eng.decode_plan_dev(d_arena.data_ptr(), in_off[:-1], sizes, 0)
+    st = plan.run_dev(view.data_ptr(), out_off, caps)
+    torch.cuda.synchronize()
+    host = view.cpu().numpy()
+    for i, (oi, opcm, _) in enumerate(expect):
+        assert st[i] == oi["status"] and np.array_equal(host[int(out_off[i]):int(out_off[i]) + caps[i]], opcm), i
+    assert (big[:3].cpu().numpy() == -21846).all()
+    plan.close()
+    import qoaudio_b200._native as NN
+    with pytest.raises(NN.NativeError):
+        eng.decode_plan_dev(d_arena.data_ptr() + 8, in_off[:-1], sizes, 0)
+    enc_out = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    pcm_d = torch.zeros(64, dtype=torch.int16, device="cuda")
+    with pytest.raises(NN.NativeError):              # 8-byte slice stores need an 8-byte aligned output arena
+        eng.encode_all_batch_dev([(1, 8000, 20)], pcm_d.data_ptr(), [0], [20], enc_out.data_ptr() + 4, [0], [4096])
 
 
 def test_device_encode_chunked_equals_one_shot(eng):
