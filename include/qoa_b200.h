@@ -200,6 +200,12 @@ int qoa_b200_decode_plan_run(qoa_b200_decode_plan *plan, int16_t *const *out, co
 int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t *d_out, const uint64_t *out_off,
                                  const size_t *out_cap, int32_t *status, void *stream);
 
+/* Sizes ONE host-resident stream without a GPU: walks its frame headers exactly like the index pre-pass does on the
+ * device (QoaDecoder::new + decode_frame_header_and_lms, src/lib.rs:127-169, :205-289) and fills *info (status,
+ * channels, sample_rate, info->samples = the i16 values a decode yields, frames, ...).  Header parsing only: no sample is
+ * decoded on the CPU.  This is what a caller of the one-call entry points below uses to allocate out[i]. */
+int qoa_b200_probe(const uint8_t *qoa, size_t len, int mode, qoa_b200_stream_info *info);
+
 /* One-call convenience for HOST buffers: plan_create + plan_run + destroy.  info may be NULL. */
 int qoa_b200_decode_all_batch(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n, int mode,
                               int16_t *const *out, const size_t *out_cap, qoa_b200_stream_info *info,

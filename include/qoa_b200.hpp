@@ -158,6 +158,30 @@ private:
     qoa_b200_ctx *ctx_ = nullptr;
 };
 
+// Every GPU of the box from one process: batches are cut into contiguous ranges of streams, one per device, balanced by
+// work; no collective (QoaEncoder / QoaDecoder hold only their own state, :59-68, :85-91).  Pass it to encode_all_batch /
+// decode_all_batch instead of an Engine.
+class MultiEngine {
+public:
+    explicit MultiEngine(const std::vector<int> &devices = {}) // empty: every visible device
+    {
+        const int rc = qoa_b200_ctx_create_multi(devices.empty() ? nullptr : devices.data(), (int)devices.size(), &m_);
+        if (rc != 0) throw EngineError(rc, std::string("qoa_b200_ctx_create_multi: ") + qoa_b200_mctx_last_error(nullptr));
+    }
+    ~MultiEngine() { qoa_b200_mctx_destroy(m_); }
+    MultiEngine(const MultiEngine &) = delete;
+    MultiEngine &operator=(const MultiEngine &) = delete;
+    qoa_b200_mctx *handle() const { return m_; }
+    int device_count() const { return qoa_b200_mctx_device_count(m_); }
+    void check(int rc, const char *what) const
+    {
+        if (rc != 0) throw EngineError(rc, std::string(what) + ": " + qoa_b200_mctx_last_error(m_));
+    }
+
+private:
+    qoa_b200_mctx *m_ = nullptr;
+};
+
 namespace detail {
 inline qoa_b200_desc c_desc(const QoaDesc &d) { return {d.channels, d.sample_rate, d.samples}; }
 inline void validate(const QoaDesc &d) // QoaEncoder::new, :336-345 (this order)
@@ -181,9 +205,23 @@ inline void put_file_header(uint8_t *p, uint32_t samples) // :404-408
 
 using EncodeResult = std::variant<std::vector<uint8_t>, EncodeError>;
 
-// Batched encode_all: one result per stream; a failing stream never aborts the batch.
+namespace detail {
+inline int call_encode_all(Engine &e, const qoa_b200_desc *d, const int16_t *const *pcm, const size_t *pl, uint8_t *const *out,
+                           const size_t *cap, size_t *len, int32_t *st, size_t n)
+{
+    return qoa_b200_encode_all_batch(e.handle(), d, pcm, pl, out, cap, len, st, n);
+}
+inline int call_encode_all(MultiEngine &e, const qoa_b200_desc *d, const int16_t *const *pcm, const size_t *pl,
+                           uint8_t *const *out, const size_t *cap, size_t *len, int32_t *st, size_t n)
+{
+    return qoa_b200_mctx_encode_all_batch(e.handle(), d, pcm, pl, out, cap, len, st, n);
+}
+} // namespace detail
+
+// Batched encode_all: one result per stream; a failing stream never aborts the batch.  EngineT = Engine | MultiEngine.
+template <typename EngineT>
 inline std::vector<EncodeResult> encode_all_batch(const std::vector<std::pair<const std::vector<int16_t> *, QoaDesc>> &items,
-                                                  Engine &eng = Engine::shared())
+                                                  EngineT &eng)
 {
     const size_t n = items.size();
     std::vector<qoa_b200_desc> descs(n);
@@ -203,8 +241,8 @@ inline std::vector<EncodeResult> encode_all_batch(const std::vector<std::pair<co
         cap[i] = out[i].size();
     }
     if (n)
-        eng.check(qoa_b200_encode_all_batch(eng.handle(), descs.data(), pcm.data(), pcm_len.data(), outp.data(), cap.data(),
-                                            len.data(), status.data(), n),
+        eng.check(detail::call_encode_all(eng, descs.data(), pcm.data(), pcm_len.data(), outp.data(), cap.data(), len.data(),
+                                          status.data(), n),
                   "qoa_b200_encode_all_batch");
     std::vector<EncodeResult> res;
     res.reserve(n);
@@ -217,6 +255,11 @@ inline std::vector<EncodeResult> encode_all_batch(const std::vector<std::pair<co
         }
     }
     return res;
+}
+
+inline std::vector<EncodeResult> encode_all_batch(const std::vector<std::pair<const std::vector<int16_t> *, QoaDesc>> &items)
+{
+    return encode_all_batch(items, Engine::shared());
 }
 
 inline std::vector<uint8_t> encode_all(const std::vector<int16_t> &sample_data, const QoaDesc &desc,
@@ -327,6 +370,39 @@ inline std::vector<DecodeResult> decode_all_batch(const std::vector<std::vector<
         cap[i] = out[i].size();
     }
     eng.check(qoa_b200_decode_plan_run(plan, outp.data(), cap.data(), status.data()), "qoa_b200_decode_plan_run");
+    res.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (status[i] != QOA_B200_OK)
+            res.emplace_back(DecodeError(DecodeError::from_status(status[i])));
+        else
+            res.emplace_back(DecodedQoa{uint8_t(info[i].channels), info[i].sample_rate, std::move(out[i])});
+    }
+    return res;
+}
+
+// The same on every device of a MultiEngine: output sizes come from qoa_b200_probe (a host-side walk of the frame headers,
+// no sample decoded), the samples from the sharded one-call path.
+inline std::vector<DecodeResult> decode_all_batch(const std::vector<std::vector<uint8_t>> &streams, MultiEngine &eng)
+{
+    const size_t n = streams.size();
+    std::vector<DecodeResult> res;
+    if (n == 0) return res;
+    std::vector<const uint8_t *> qoa(n);
+    std::vector<size_t> len(n), cap(n);
+    std::vector<qoa_b200_stream_info> info(n);
+    std::vector<std::vector<int16_t>> out(n);
+    std::vector<int16_t *> outp(n);
+    std::vector<int32_t> status(n);
+    for (size_t i = 0; i < n; ++i) {
+        qoa[i] = streams[i].data(), len[i] = streams[i].size();
+        eng.check(qoa_b200_probe(qoa[i], len[i], QOA_B200_DECODE_ALL, &info[i]), "qoa_b200_probe");
+        out[i].resize(info[i].samples);
+        outp[i] = out[i].data();
+        cap[i] = out[i].size();
+    }
+    eng.check(qoa_b200_mctx_decode_all_batch(eng.handle(), qoa.data(), len.data(), n, QOA_B200_DECODE_ALL, outp.data(),
+                                             cap.data(), info.data(), status.data()),
+              "qoa_b200_mctx_decode_all_batch");
     res.reserve(n);
     for (size_t i = 0; i < n; ++i) {
         if (status[i] != QOA_B200_OK)

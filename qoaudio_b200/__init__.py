@@ -8,4 +8,4 @@ from .api import (MAX_SLICES_PER_CHANNEL_PER_FRAME, QOA_FRAME_LEN, QOA_HEADER_SI
                   FrameHeader, ProcessingMode, QoaDecoder, QoaDesc, QoaEncoder, QoaEncoderBatch, QoaItem, decode_all,
                   decode_all_batch, encode_all, encode_all_batch, open_and_decode_all)
 from . import wavio  # noqa: F401
-from .engine import DecodePlan, EncoderBatch, Engine, MultiEngine, default_engine, partition  # noqa: F401
+from .engine import DecodePlan, EncoderBatch, Engine, MultiEngine, default_engine, partition, probe  # noqa: F401

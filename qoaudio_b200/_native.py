@@ -59,6 +59,7 @@ SYMBOLS = {
     "qoa_b200_decode_plan_frame_headers": (_SZ, [_P, _SZ, _P, _SZ]),
     "qoa_b200_decode_plan_run": (C.c_int, [_P, _P, _P, _P]),
     "qoa_b200_decode_plan_run_dev": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "qoa_b200_probe": (C.c_int, [_P, _SZ, C.c_int, _P]),
     "qoa_b200_decode_all_batch": (C.c_int, [_P, _P, _P, _SZ, C.c_int, _P, _P, _P, _P]),
     "qoa_b200_gen_pcm_dev": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64,
                                        C.c_int, _P]),

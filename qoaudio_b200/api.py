@@ -309,8 +309,8 @@ class QoaDecoder:
         are whole frames therefore decodes exactly as a stateless call does, which is what this method is.  Bytes that
         are NOT whole frames behave as in the reference, too: a frame cut after its 8-byte header is IoError
         (UnexpectedEof, and the reference decoder is unusable afterwards, :666-667), and 1-7 trailing bytes are consumed
-        silently (read_exact on a Cursor moves to the end on a short read - the semantics the oracle restates,
-        oracle/qoa_oracle.c rd()); neither implementation can resume a frame that was split across two calls."""
+        silently (read_exact on a Cursor moves to the end on a short read); neither implementation can resume a frame that
+        was split across two calls."""
         if not self._frame_mode:
             raise TypeError("decode_frame is only available on QoaDecoder.new_streaming()")
         infos, outs = self._eng.decode_batch([bytes(frame_data)], N.DECODE_FRAMES)

@@ -995,6 +995,13 @@ int plan_index(qoa_b200_ctx *ctx, qoa_b200_decode_plan *plan, const uint64_t *in
 
 } // namespace
 
+extern "C" int qoa_b200_probe(const uint8_t *qoa, size_t len, int mode, qoa_b200_stream_info *info)
+{
+    if (!info || (len && !qoa) || mode < QOA_B200_DECODE_ITER || mode > QOA_B200_DECODE_FRAMES) return QOA_B200_E_ARG;
+    qoa::probe_stream(qoa, len, mode, info);
+    return 0;
+}
+
 extern "C" int qoa_b200_decode_plan_create_dev(qoa_b200_ctx *ctx, const uint8_t *d_qoa, const uint64_t *in_off,
                                                const size_t *len, size_t n, int mode, void *stream,
                                                qoa_b200_decode_plan **out)

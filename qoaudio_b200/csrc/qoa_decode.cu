@@ -25,14 +25,28 @@ namespace qoa {
 // Index pre-pass
 // ================================================================================================================
 
-__device__ __forceinline__ uint32_t ld_be32(const uint8_t *p) // 4-byte aligned
+// Big-endian loads usable from both sides: the walk below also runs on the host for qoa_b200_probe (header parsing only;
+// no sample is ever decoded on the CPU).
+__host__ __device__ __forceinline__ uint32_t ld_be32(const uint8_t *p) // 4-byte aligned on the device
 {
+#ifdef __CUDA_ARCH__
     return bswap32(__ldg(reinterpret_cast<const uint32_t *>(p)));
+#else
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+#endif
+}
+__host__ __device__ __forceinline__ uint2 ld_be64(const uint8_t *p) // 8-byte aligned on the device; (hi, lo)
+{
+#ifdef __CUDA_ARCH__
+    return ldg_be64(p);
+#else
+    return make_uint2(ld_be32(p), ld_be32(p + 4));
+#endif
 }
 
 // Walks one stream exactly like QoaDecoder::new + Iterator::next would, without decoding samples.
 template <bool FILL>
-__device__ void walk_stream(const uint8_t *__restrict__ arena, uint64_t off, uint64_t len, int mode, uint32_t stream,
+__host__ __device__ void walk_stream(const uint8_t *__restrict__ arena, uint64_t off, uint64_t len, int mode, uint32_t stream,
                             FrameRec *__restrict__ recs, qoa_b200_stream_info *__restrict__ out)
 {
     const uint8_t *p = arena + off;
@@ -83,7 +97,7 @@ __device__ void walk_stream(const uint8_t *__restrict__ arena, uint64_t off, uin
             break;
         }
         const uint64_t frame_pos = pos;
-        const uint2 hw = ldg_be64(p + pos);
+        const uint2 hw = ld_be64(p + pos);
         pos += 8;
         const uint32_t ch = hw.x >> 24;            // :217
         const uint32_t rate = hw.x & 0xffffffu;     // :218
@@ -151,8 +165,8 @@ __device__ void walk_stream(const uint8_t *__restrict__ arena, uint64_t off, uin
             recs[table_frames] = r;
         }
         table_frames++;
-        max_ch = max(max_ch, ch);
-        min_ch = min(min_ch, ch);
+        max_ch = ch > max_ch ? ch : max_ch;
+        min_ch = ch < min_ch ? ch : min_ch;
         aligned = aligned && ((samples & 7) == 0);
         samples += (uint64_t)nsamp * ch;
         if (truncated) {
@@ -1189,6 +1203,11 @@ static cudaError_t launch_fast(const uint8_t *d_arena, const FrameRec *d_recs, u
     decode_fast_kernel<CH, S, NB, THREADS><<<(unsigned)blocks, THREADS, smem, s>>>(
         d_arena, d_recs, n_frames, d_out_base, d_out, map, map_rem, map32, map32_rem, use_map);
     return cudaGetLastError();
+}
+
+void probe_stream(const uint8_t *qoa, uint64_t len, int mode, qoa_b200_stream_info *info)
+{
+    walk_stream<false>(qoa, 0, len, mode, 0, nullptr, info);
 }
 
 cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64_t n_frames, uint32_t max_ch,

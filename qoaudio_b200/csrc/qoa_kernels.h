@@ -37,6 +37,9 @@ cudaError_t launch_decode(const uint8_t *d_arena, const FrameRec *d_recs, uint64
                           uint32_t uniform_ch, const uint64_t *d_out_base, int16_t *d_out, uint64_t out_bytes,
                           cudaStream_t s, int *n_launches);
 
+// The index walk of ONE stream on the host (frame headers only): what qoa_b200_probe returns.
+void probe_stream(const uint8_t *qoa, uint64_t len, int mode, qoa_b200_stream_info *info);
+
 // ---- encode --------------------------------------------------------------------------------------------------
 // Per-stream encode job (device table).
 struct EncJob {

@@ -399,6 +399,15 @@ class MultiEngine(Engine):
             msg = N.lib().qoa_b200_mctx_last_error(self._h)
             raise N.NativeError(f"qoa_b200_mctx_{what} failed with {rc}: {msg.decode() if msg else '?'}")
 
+    def decode_batch(self, streams, mode=N.DECODE_ITER):
+        """Decode host-resident streams of unknown size on every device: sizes come from qoa_b200_probe (host-side header
+        walk), the samples from the sharded one-call path.  Returns (infos, list of np.int16 arrays) like Engine."""
+        bufs = [np.frombuffer(bytes(s), dtype=np.uint8) if not isinstance(s, np.ndarray) else s for s in streams]
+        infos = [probe(b, mode) for b in bufs]
+        info, status, outs = self.decode_all_batch(bufs, [i["samples"] for i in infos], mode)
+        names = INFO_DTYPE.names
+        return [{k: (bool(r[k]) if k == "streaming" else int(r[k])) for k in names} for r in info], outs
+
     def partition(self, weights):
         """The contiguous split the batch calls use: [(begin, end), ...] per device."""
         return partition(weights, len(self.devices))
@@ -410,6 +419,17 @@ class MultiEngine(Engine):
         e._h = C.c_void_p(N.lib().qoa_b200_mctx_ctx(self._h, i))
         e.close = lambda: None
         return e
+
+
+def probe(stream, mode=N.DECODE_ITER):
+    """qoa_b200_probe: per-stream info dict (status, channels, sample_rate, samples, frames, ...) from a host-side walk
+    of the frame headers (no GPU, no sample decoded) - what a caller needs to size the output of a one-call decode."""
+    buf = np.frombuffer(bytes(stream), dtype=np.uint8) if not isinstance(stream, np.ndarray) else np.ascontiguousarray(stream, dtype=np.uint8)
+    info = np.zeros(1, dtype=INFO_DTYPE)
+    rc = N.lib().qoa_b200_probe(C.c_void_p(buf.ctypes.data if buf.size else None), buf.size, mode, C.c_void_p(info.ctypes.data))
+    if rc != 0:
+        raise ValueError(f"qoa_b200_probe failed with {rc}")
+    return {k: (bool(info[0][k]) if k == "streaming" else int(info[0][k])) for k in INFO_DTYPE.names}
 
 
 def partition(weights, parts):

@@ -79,6 +79,7 @@ extern "C" {
     pub fn qoa_b200_gen_qoa_dev(ctx: *mut qoa_b200_ctx, d_qoa: *mut u8, stride: u64, n_streams: u64, first_stream: u64,
         channels: u32, sample_rate: u32, samples: u32, seed: u64, stream: *mut c_void) -> c_int;
     pub fn qoa_b200_int_issue_peak(ctx: *mut qoa_b200_ctx, kind: c_int, thread_ops_per_s: *mut f64) -> c_int;
+    pub fn qoa_b200_probe(qoa: *const u8, len: usize, mode: c_int, info: *mut qoa_b200_stream_info) -> c_int;
     // several GPUs from one process (batches sharded by stream, no collective)
     pub fn qoa_b200_ctx_create_multi(devices: *const c_int, n: c_int, mctx: *mut *mut qoa_b200_mctx) -> c_int;
     pub fn qoa_b200_mctx_destroy(mctx: *mut qoa_b200_mctx);

@@ -156,6 +156,24 @@ int main(int argc, char **argv)
         CHECK(std::holds_alternative<DecodeError>(decs[1]));
         CHECK(std::holds_alternative<DecodedQoa>(decs[2]) && std::get<DecodedQoa>(decs[2]).samples == dec.samples);
         dump(dir + "/mono.dec", std::get<DecodedQoa>(decs[0]).samples);
+        // the same batch through a multi-device engine (two contexts; with one visible GPU both sit on device 0)
+        int ndev = 0;
+        {
+            MultiEngine all; // no list: every visible device
+            ndev = all.device_count();
+            CHECK(ndev >= 1);
+        }
+        MultiEngine multi(ndev >= 2 ? std::vector<int>{0, 1} : std::vector<int>{0, 0});
+        CHECK(multi.device_count() == 2);
+        auto menc = encode_all_batch({{&pcm, desc}, {&none, QoaDesc{0, 8000, 1}}, {&mpcm, mono}}, multi);
+        CHECK(std::holds_alternative<std::vector<uint8_t>>(menc[0]) && std::get<std::vector<uint8_t>>(menc[0]) == one_shot);
+        CHECK(std::holds_alternative<EncodeError>(menc[1]) && std::get<EncodeError>(menc[1]).kind == EncodeError::InvalidChannels);
+        CHECK(std::holds_alternative<std::vector<uint8_t>>(menc[2]) && std::get<std::vector<uint8_t>>(menc[2]) == mq);
+        auto mdecs = decode_all_batch({mq, std::vector<uint8_t>{1, 2, 3}, one_shot}, multi);
+        CHECK(std::holds_alternative<DecodedQoa>(mdecs[0]) &&
+              std::get<DecodedQoa>(mdecs[0]).samples == std::get<DecodedQoa>(decs[0]).samples);
+        CHECK(std::holds_alternative<DecodeError>(mdecs[1]));
+        CHECK(std::holds_alternative<DecodedQoa>(mdecs[2]) && std::get<DecodedQoa>(mdecs[2]).samples == dec.samples);
     }
     {
         dump(dir + "/file.qoa", one_shot);

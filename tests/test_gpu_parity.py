@@ -664,6 +664,10 @@ def test_multi_device_context(eng, N):
     assert (dst == dst1).all() and dst[-1] == N.DEC_NOT_QOA_FILE and (info == info1).all()
     for i, s in enumerate(streams[:-1]):
         assert np.array_equal(outs[i], outs1[i]) and np.array_equal(outs[i], ob.decode_all(s.tobytes())[1]), i
+    infos2, outs2 = m.decode_batch(streams)          # sizes from qoa_b200_probe (host-side header walk), iterator mode
+    for i, s in enumerate(streams):
+        oi, opcm = ob.decode_iter(s.tobytes())[:2]
+        assert infos2[i]["status"] == oi["status"] and infos2[i]["samples"] == oi["samples"] and np.array_equal(outs2[i], opcm), i
     # the split is the documented one: contiguous, balanced by encoded length
     parts = m.partition([len(s) for s in streams])
     assert parts[0][0] == 0 and parts[-1][1] == len(streams) and all(a[1] == b[0] for a, b in zip(parts, parts[1:]))

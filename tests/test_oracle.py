@@ -325,3 +325,37 @@ def test_golden_dump_checker(tmp_path):
     main_rs = open(os.path.join(ROOT, "rust", "golden-dump", "src", "main.rs")).read()
     for token in (".dec.pcm", ".decoded.pcm", ".reencoded.qoa", "encode_all", "decode_all", "encode_frame"):
         assert token in main_rs
+
+
+def test_probe_matches_oracle_walk(fixture_bytes):
+    """qoa_b200_probe walks frame headers on the HOST (no GPU, no sample decoded) with the code the index pre-pass runs
+    on the device; its info must equal what the oracle's decoder reports, for good files, every truncation of small
+    files and malformed headers, in all three modes."""
+    import qoaudio_b200 as q
+    keys = ("status", "streaming", "header_samples", "channels", "sample_rate", "samples", "frames")
+
+    def same(blob, mode):
+        got = q.probe(blob, mode)
+        oi = (ob.decode_iter(blob)[0] if mode == 0 else ob.decode_all(blob)[0])
+        assert {k: got[k] for k in keys} == {k: oi[k] for k in keys}, (len(blob), mode, got, oi)
+
+    same(fixture_bytes, 0)
+    same(fixture_bytes, 1)
+    same(fixture_bytes[:100000], 0)
+    small = [ob.encode_all(signals.synth_pcm(3, i, ch, n), ch, 8000, n)[1] for i, (ch, n) in
+             enumerate([(1, 45), (2, 5121), (3, 20), (8, 21)])]
+    for blob in small:
+        for cut in list(range(0, min(len(blob), 200))) + [len(blob) - 1, len(blob)]:
+            same(blob[:cut], 0)
+            same(blob[:cut], 1)
+    rng = np.random.default_rng(9)
+    base = bytearray(small[1])
+    for _ in range(300):                       # header mutations: the shapes of fuzz/fuzz_targets/iter_all.rs
+        m = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            m[int(rng.integers(0, 40))] ^= 1 << int(rng.integers(0, 8))
+        same(bytes(m), int(rng.integers(0, 2)))
+    streaming = small[0][:4] + bytes(4) + small[0][8:]  # header samples == 0: Streaming mode and its dummy first header
+    same(streaming, 0)
+    same(streaming, 1)
+    assert q.probe(small[1][8:], 2)["samples"] == 2 * 5121  # DECODE_FRAMES: frames without the file header
