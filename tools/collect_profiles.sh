@@ -6,7 +6,7 @@ P=profiles
 cp $O/final_bench_n1.json $P/${R}_bench_n1.json
 cp $O/final_bench_ref.json $P/${R}_bench_reference_arm.json
 cp $O/final_launches.csv $P/${R}_launches.csv
-python tools/summarize_launches.py $O/final_launches.csv > $P/${R}_launches_summary.txt
+python tools/summarize_launches.py $O/final_launches.csv "python bench.py --steps 3 --warmup 3 --streams 2048 --enc-streams 2048 --no-cpu --e2e-streams 32 --no-single --no-extras" > $P/${R}_launches_summary.txt
 python tools/summarize_ncu.py $O/final_dec.ncu-rep > $P/${R}_decode_fast_kernel_ncu_full.txt
 python tools/summarize_ncu.py $O/final_enc.ncu-rep > $P/${R}_encode_kernel_ncu_full.txt
 for c in 1 6 8; do python tools/summarize_ncu.py $O/final_dec_${c}ch.ncu-rep > $P/${R}_decode_${c}ch_ncu_full.txt; done
