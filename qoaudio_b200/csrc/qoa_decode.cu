@@ -903,11 +903,14 @@ static int make_out_map(CUtensorMap *map, void *d_out, uint64_t out_bytes, uint3
 }
 
 // ---- uniform multi-channel batches (3..8 channels) ---------------------------------------------------------------
-// One thread = one (frame, channel pair): the same two-chain slice loop as stereo (an odd channel count leaves the
-// last pair with one live chain).  The P = ceil(ch / 2) lanes of a frame are neighbours in the warp, 32 / P frames
-// per warp.  Every lane writes its pair's samples into its FRAME's row of a per-warp shared-memory tile
-// ([frames][S slices x 20 samples x ch] interleaved i16; S = 1 for even, 2 for odd channel counts
-// so that a row is a multiple of 16 bytes).  After S slices the tile leaves
+// One thread = two channel chains, the same two-chain slice loop as stereo.  Even channel counts: the lane owns a
+// channel pair of one frame, the ch / 2 lanes of a frame are neighbours.  Odd channel counts: frames are taken two at
+// a time and the 2 x (ch / 2) + 1 = ch lanes of such a frame pair are (ch / 2) pairs of the first frame, (ch / 2)
+// pairs of the second, and ONE lane whose two chains are the last channel of each of the two frames - every chain a
+// lane computes is useful (round 1 gave every frame its own half-empty last pair: 3 channels used 3/4 of the
+// arithmetic, 5 channels 5/6).  Every chain writes its samples into its FRAME's row of a per-warp shared-memory tile
+// ([frames][S slices x 20 samples x ch] interleaved i16; S = 1 for even, 2 for odd channel counts so that a row is a
+// multiple of 16 bytes).  After S slices the tile leaves
 //   * through ONE 2-D tensor store (rows = frames, box = one group of one frame's interleaved PCM) when the warp's
 //     frames are full-size neighbours in one stream - no copy-out instructions (round 1 copied every tile out with
 //     LDS.128 + STG.128: 368 of 1097 instructions per slice for 8 channels);
@@ -921,20 +924,27 @@ constexpr int kMultiTileBytes = 5632; // largest tile: 4 channels = 16 frames x 
 
 template <int CH>
 struct MultiCfg {
-    static constexpr uint32_t P = (CH + 1) / 2;                       // channel pairs per frame
-    static constexpr uint32_t kFpw = 32 / P;                          // frames per warp
-    static constexpr uint32_t S = (CH % 2 == 0) ? 1u : 2u;            // slices per tile row
-    static constexpr uint32_t kSliceBytes = kSliceLen * CH * 2;       // interleaved PCM of one slice of one frame
+    static constexpr bool kOdd = (CH & 1) != 0;
+    static constexpr uint32_t H = CH / 2;                              // whole channel pairs per frame
+    static constexpr uint32_t kGroupLanes = kOdd ? CH : H;             // lanes per frame (even) / per frame pair (odd)
+    static constexpr uint32_t kGroups = 32 / kGroupLanes;
+    static constexpr uint32_t kFpw = kOdd ? 2 * kGroups : kGroups;     // frames per warp
+    static constexpr uint32_t S = kOdd ? 2u : 1u;                      // slices per tile row
+    static constexpr uint32_t kSliceBytes = kSliceLen * CH * 2;        // interleaved PCM of one slice of one frame
     static constexpr uint32_t kRowBytes = S * kSliceBytes;
     static constexpr uint32_t kPadPitch = kRowBytes + (((kRowBytes >> 4) & 1) ? 0 : 16); // copy path: odd multiple of 16
-    static constexpr uint32_t kOutRowBytes = kFrameLen * CH * 2;      // PCM bytes of one full frame = tensor-map row pitch
+    static constexpr uint32_t kOutRowBytes = kFrameLen * CH * 2;       // PCM bytes of one full frame = tensor-map row pitch
     static_assert(kRowBytes % 16 == 0 && kFpw * kPadPitch <= (uint32_t)kMultiTileBytes, "tile layout");
-    static_assert(kRowBytes / 4 <= 256 && (kSlicesPerFrame % S) == 0, "tensor-map box limits");
+    static_assert(kRowBytes / 4 <= 256 && kFpw <= 256 && (kSlicesPerFrame % S) == 0, "tensor-map box limits");
 };
 
 __device__ __forceinline__ void cp_async8(uint32_t saddr, const void *gptr)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((uint16_t)v) : "memory");
 }
 
 template <int CH>
@@ -946,68 +956,91 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
     using Cfg = MultiCfg<CH>;
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr int kWarps = kMultiThreads / 32;
-    constexpr uint32_t ch = CH, P = Cfg::P, fpw = Cfg::kFpw, S = Cfg::S, row_bytes = Cfg::kRowBytes;
+    constexpr uint32_t ch = CH, fpw = Cfg::kFpw, S = Cfg::S, row_bytes = Cfg::kRowBytes;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t pad = (kLutAlign - (smem_u32(smem_raw) & (kLutAlign - 1))) & (kLutAlign - 1);
     uint8_t *smem = smem_raw + pad;
     fill_lut(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t fl = lane / P, p = lane - fl * P; // frame within the warp, pair within the frame
-    const uint64_t fi = ((uint64_t)blockIdx.x * kWarps + warp) * fpw + fl;
+    // this lane's two chains: (frame fa, channel ca) and (frame fb, channel cb); frames are indices inside the warp
+    const uint32_t g = lane / Cfg::kGroupLanes, q = lane - g * Cfg::kGroupLanes;
+    uint32_t fa, fb, ca, cb;
+    if (!Cfg::kOdd) {
+        fa = fb = g;
+        ca = 2 * q;
+        cb = ca + 1;
+    } else if (q < 2 * Cfg::H) {
+        fa = fb = 2 * g + (q >= Cfg::H ? 1u : 0u);
+        ca = 2 * (q >= Cfg::H ? q - Cfg::H : q);
+        cb = ca + 1;
+    } else { // the odd channels of both frames of the pair
+        fa = 2 * g;
+        fb = fa + 1;
+        ca = cb = ch - 1;
+    }
+    const bool lane_on = g < Cfg::kGroups;
+    const bool same = fa == fb;
+    const uint64_t f0 = ((uint64_t)blockIdx.x * kWarps + warp) * fpw;
 
-    uint32_t nsamp = 0;
-    uint64_t out_byte = 0;
-    FrameRec rec;
-    rec.in_off = 0;
-    if (fl < fpw && fi < n_frames) {
-        rec = recs[fi];
-        const uint64_t ob = out_base[rec.stream];
+    uint32_t nsamp_a = 0, nsamp_b = 0;
+    uint64_t ob_a = 0, ob_b = 0; // byte offsets of the two frames' PCM inside the output arena
+    FrameRec ra_, rb_;
+    ra_.in_off = rb_.in_off = 0;
+    if (lane_on && f0 + fa < n_frames) {
+        ra_ = recs[f0 + fa];
+        const uint64_t ob = out_base[ra_.stream];
         if (ob != ~0ull) {
-            nsamp = rec.nsamp;
-            out_byte = (ob + rec.out_rel) * 2;
+            nsamp_a = ra_.nsamp;
+            ob_a = (ob + ra_.out_rel) * 2;
         }
     }
-    uint8_t *op = reinterpret_cast<uint8_t *>(out) + out_byte;
-    const uint32_t nslices = (nsamp + kSliceLen - 1) / kSliceLen;
-    const uint32_t nsl_max = __reduce_max_sync(kFull, nslices);
+    if (same) {
+        rb_ = ra_;
+        nsamp_b = nsamp_a;
+        ob_b = ob_a;
+    } else if (lane_on && f0 + fb < n_frames) {
+        rb_ = recs[f0 + fb];
+        const uint64_t ob = out_base[rb_.stream];
+        if (ob != ~0ull) {
+            nsamp_b = rb_.nsamp;
+            ob_b = (ob + rb_.out_rel) * 2;
+        }
+    }
+    const uint32_t nsl_a = (nsamp_a + kSliceLen - 1) / kSliceLen, nsl_b = (nsamp_b + kSliceLen - 1) / kSliceLen;
+    const uint32_t nsl_max = __reduce_max_sync(kFull, max(nsl_a, nsl_b));
     if (nsl_max == 0) return;
     // Tensor-store mode (warp-uniform): every frame of the warp is a full frame and frame f sits f rows below frame 0.
-    const uint64_t out00 = __shfl_sync(kFull, out_byte, 0);
+    const uint64_t out00 = __shfl_sync(kFull, ob_a, 0);
     const bool tma = use_map == 2 &&
-                     __all_sync(kFull, fl >= fpw || (nsamp == (uint32_t)kFrameLen &&
-                                                     out_byte == out00 + (uint64_t)fl * Cfg::kOutRowBytes));
+                     __all_sync(kFull, !lane_on || (nsamp_a == (uint32_t)kFrameLen && nsamp_b == (uint32_t)kFrameLen &&
+                                                    ob_a == out00 + (uint64_t)fa * Cfg::kOutRowBytes &&
+                                                    ob_b == out00 + (uint64_t)fb * Cfg::kOutRowBytes));
     const uint32_t pitch = tma ? row_bytes : Cfg::kPadPitch;
     int map_c1 = (int)(out00 / Cfg::kOutRowBytes), map_c0 = (int)((out00 % Cfg::kOutRowBytes) / 4);
 
-    const uint32_t c0 = 2 * p;
-    const bool two = c0 + 1 < ch; // the last pair of an odd channel count has one live chain (the other mirrors it)
-    const uint8_t *fp = arena + rec.in_off;
+    const uint8_t *fp_a = arena + ra_.in_off, *fp_b = arena + rb_.in_off;
     Chain a, b;
     a = Chain{0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1};
     b = a;
-    if (nslices) {
-        load_lms(a, fp + 8 + 16 * c0);
-        load_lms(b, fp + 8 + 16 * (two ? c0 + 1 : c0));
-    }
-    const uint8_t *sp = fp + 8 + 16 * ch + 8 * c0; // this pair's word(s) of slice 0; slice k is k * ch * 8 bytes further
+    if (nsl_a) load_lms(a, fp_a + 8 + 16 * ca);
+    if (nsl_b) load_lms(b, fp_b + 8 + 16 * cb);
+    // the chains' words of slice 0; slice k is k * ch * 8 bytes further
+    const uint8_t *sp_a = fp_a + 8 + 16 * ch + 8 * ca, *sp_b = fp_b + 8 + 16 * ch + 8 * cb;
     const uint32_t lane_row = smem_u32(smem) + (lane & 15) * 8;
     // shared memory after the LUT: per warp [tile: frames x pitch <= kMultiTileBytes][ring: 4 x 32 x 16][row table: 32 x 16]
     const uint32_t warp_base = smem_u32(smem + kLutBytes) + warp * (kMultiTileBytes + 2048 + 512);
     const uint32_t tile = warp_base;
     const uint32_t in_ring = warp_base + kMultiTileBytes + lane * 16;
     const uint32_t rows_meta = warp_base + kMultiTileBytes + 2048;
-    if (p == 0) { // one table entry per frame: {PCM pointer, nsamp}
-        const uint64_t p64 = reinterpret_cast<uint64_t>(op);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rows_meta + fl * 16), "r"((uint32_t)p64),
-                     "r"((uint32_t)(p64 >> 32)), "r"(fl < fpw ? nsamp : 0u), "r"(0u)
+    if (lane_on && ca == 0) { // one table entry per frame: {PCM pointer, nsamp}; the lane of channel pair 0 writes it
+        const uint64_t p64 = reinterpret_cast<uint64_t>(reinterpret_cast<uint8_t *>(out) + ob_a);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rows_meta + fa * 16), "r"((uint32_t)p64),
+                     "r"((uint32_t)(p64 >> 32)), "r"(nsamp_a), "r"(0u)
                      : "memory");
     }
-    auto fetch = [&](uint32_t k) { // slice k's word(s) into ring slot k % 4
-        if (k < nslices) {
-            const uint8_t *g = sp + (uint64_t)k * ch * 8;
-            cp_async8(in_ring + (k & 3) * 512, g);
-            if (two) cp_async8(in_ring + (k & 3) * 512 + 8, g + 8);
-        }
+    auto fetch = [&](uint32_t k) { // slice k's words into ring slot k % 4
+        if (k < nsl_a) cp_async8(in_ring + (k & 3) * 512, sp_a + (uint64_t)k * ch * 8);
+        if (k < nsl_b) cp_async8(in_ring + (k & 3) * 512 + 8, sp_b + (uint64_t)k * ch * 8);
         cp_async_commit();
     };
     fetch(0);
@@ -1015,18 +1048,21 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
     fetch(2);
     __syncwarp();
 
-    const uint32_t row = tile + fl * pitch + c0 * 2; // this pair's first sample inside its frame's row
+    // the chains' first samples inside their frames' rows
+    const uint32_t row_a0 = tile + fa * pitch + ca * 2, row_b0 = tile + fb * pitch + cb * 2;
     uint32_t in_row = 0, first = 0;
 #pragma unroll 1
     for (uint32_t k = 0; k < nsl_max; ++k) {
         fetch(k + 3);
         cp_async_wait<3>(); // slice k's words have landed
         uint32_t o[20];
-        if (k < nslices) {
-            const uint2 ra = lds64(in_ring + (k & 3) * 512);
-            const uint2 rb = two ? lds64(in_ring + (k & 3) * 512 + 8) : ra;
-            const uint2 wa = make_uint2(bswap32(ra.x), bswap32(ra.y));
-            const uint2 wb = make_uint2(bswap32(rb.x), bswap32(rb.y));
+        const bool on_a = k < nsl_a, on_b = k < nsl_b;
+        if (on_a || on_b) {
+            uint2 xa = lds64(in_ring + (k & 3) * 512), xb = lds64(in_ring + (k & 3) * 512 + 8);
+            if (!on_a) xa = xb; // a finished chain decodes its neighbour's word (valid table addresses), unused
+            if (!on_b) xb = xa;
+            const uint2 wa = make_uint2(bswap32(xa.x), bswap32(xa.y));
+            const uint2 wb = make_uint2(bswap32(xb.x), bswap32(xb.y));
             const uint32_t row_a = lane_row + (wa.x >> 28) * 1024; // sf = top nibble (:303)
             const uint32_t row_b = lane_row + (wb.x >> 28) * 1024;
             PairLoop<0>::run(a, b, row_a, row_b, wa, wb, o);
@@ -1035,17 +1071,20 @@ decode_multi_kernel(const uint8_t *__restrict__ arena, const FrameRec *__restric
             bulk_wait_read<0>();  // wait comes every slice, so it sits BEHIND the slice's arithmetic (in front of it the
             __syncwarp();         // warps spent 2.4 stall cycles per issue on it: profiles/r02_decode_multi_8ch_*.txt)
         }
-        if (k < nslices) {
-            const uint32_t dst = row + in_row * Cfg::kSliceBytes;
-            if (!(ch & 1)) { // even channel counts: the pair is one aligned 32-bit word per sample
+        const uint32_t da = row_a0 + in_row * Cfg::kSliceBytes, db = row_b0 + in_row * Cfg::kSliceBytes;
+        if (!Cfg::kOdd) { // even channel counts: the pair is one aligned 32-bit word per sample (both chains, one frame)
+            if (on_a) {
 #pragma unroll
-                for (int i = 0; i < 20; ++i) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + i * ch * 2), "r"(o[i]) : "memory");
-            } else {
+                for (int i = 0; i < 20; ++i) asm volatile("st.shared.b32 [%0], %1;" ::"r"(da + i * ch * 2), "r"(o[i]) : "memory");
+            }
+        } else {
+            if (on_a) {
 #pragma unroll
-                for (int i = 0; i < 20; ++i) {
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * ch * 2), "h"((uint16_t)(o[i] & 0xffffu)) : "memory");
-                    if (two) asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + i * ch * 2 + 2), "h"((uint16_t)(o[i] >> 16)) : "memory");
-                }
+                for (int i = 0; i < 20; ++i) sts_u16(da + i * ch * 2, o[i] & 0xffffu);
+            }
+            if (on_b) {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) sts_u16(db + i * ch * 2, o[i] >> 16);
             }
         }
         ++in_row;
