@@ -679,3 +679,103 @@ def test_multi_device_context(eng, N):
     ref = [ob.decode_all(b.tobytes())[1] for b in big[:4]]
     assert (dst == 0).all() and all(np.array_equal(o, ref[i % 4]) for i, o in enumerate(outs))
     m.close()
+
+
+def test_full_size_decode_batch_properties(eng, N):
+    """BASELINE.json configs[2] at FULL size (8192 x 60 s stereo, 104 GB of traffic) through size-independent
+    properties: (1) per-stream checksums of the whole batch decoded in one plan equal those of the same streams decoded
+    in three uneven sub-batches (different frame-table offsets, so different warps / loops see every frame); (2) decoding
+    twice is idempotent; (3) a random handful of streams equals the oracle sample for sample; (4) bytes around every
+    stream's slot stay untouched."""
+    import torch
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    S = 8192 if free > 150e9 else 1024
+    ch, rate, n = 2, 44100, 2646000
+    size = 8 + ((n + 5119) // 5120) * (8 + 16 * ch) + ((n + 19) // 20) * 8 * ch
+    stride = (size + 15) // 16 * 16
+    per = n * ch
+    slot = per + 24                                        # 24 guard values behind every stream (keeps 16-byte alignment)
+    stream = torch.cuda.current_stream().cuda_stream
+    qoa = torch.empty(S * stride, dtype=torch.uint8, device="cuda")
+    eng.gen_qoa_dev(qoa.data_ptr(), stride, S, 0, ch, rate, n, 7, stream)
+    in_off = np.arange(S, dtype=np.uint64) * np.uint64(stride)
+    lens = np.full(S, size, dtype=np.uint64)
+    out_off = np.arange(S, dtype=np.uint64) * np.uint64(slot)
+    caps = np.full(S, per, dtype=np.uint64)
+    w = torch.arange(1, 4097, dtype=torch.int32, device="cuda")
+
+    def checksums(buf):                                    # position-weighted sums per stream, int64, chunked to bound memory
+        v = buf.view(S, slot)
+        out = torch.zeros(S, dtype=torch.int64, device="cuda")
+        step = 4096 * 16                                   # 2 GB of int32 temporaries per block at S = 8192
+        for c0 in range(0, per, step):
+            c1 = min(per, c0 + step)
+            blk = v[:, c0:c1].to(torch.int32)
+            pad = (-blk.shape[1]) % 4096
+            if pad:
+                blk = torch.nn.functional.pad(blk, (0, pad))
+            out += (blk.view(S, -1, 4096) * w).sum(dim=(1, 2), dtype=torch.int64) * (1 + c0 // step)
+            del blk
+        return out, v[:, per:].clone()
+
+    def decode(ranges, fill):
+        pcm = torch.full((S * slot,), fill, dtype=torch.int16, device="cuda")
+        for b, e in ranges:
+            plan = eng.decode_plan_dev(qoa.data_ptr(), in_off[b:e], lens[b:e], N.DECODE_ALL, stream)
+            st = plan.run_dev(pcm.data_ptr(), out_off[b:e], caps[b:e], stream)
+            assert (st == 0).all() and (plan.info_array["samples"] == per).all()
+            plan.close()
+        torch.cuda.synchronize()
+        return pcm
+
+    pcm = decode([(0, S)], 1234)
+    sums, guards = checksums(pcm)
+    assert (guards == 1234).all()
+    rng = np.random.default_rng(4)
+    for s in sorted(set([0, S - 1] + [int(v) for v in rng.integers(0, S, size=6)])):
+        blob = qoa[s * stride:s * stride + size].cpu().numpy().tobytes()
+        assert np.array_equal(pcm[s * slot:s * slot + per].cpu().numpy(), ob.decode_all(blob)[1]), s
+    del pcm
+    cut1, cut2 = S // 3 + 5, (2 * S) // 3 + 11             # uneven thirds: frame-table offsets that are no multiple of 32
+    pcm2 = decode([(0, cut1), (cut1, cut2), (cut2, S)], -77)
+    sums2, guards2 = checksums(pcm2)
+    assert torch.equal(sums, sums2) and (guards2 == -77).all()
+    del pcm2
+    pcm3 = decode([(0, S)], 5)                             # idempotence
+    assert torch.equal(checksums(pcm3)[0], sums)
+
+
+def test_full_size_encode_chunking_property(eng, N):
+    """BASELINE.json configs[3] shape at full width (4096 stereo 48 kHz streams): 32 frames of every stream encoded as one
+    chunk, as 2 x 16 frames and as 5 + 27 frames (LMS state carried on the device, src/lib.rs:481-482) give identical
+    bytes for ALL streams; streams 0, 1777 and last equal the oracle."""
+    import torch
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    S = 4096 if free > 60e9 else 512
+    ch, rate, frames = 2, 48000, 32
+    n = frames * 5120
+    fbytes = 8 + 16 * ch + 2048 * ch
+    stream = torch.cuda.current_stream().cuda_stream
+    pcm = torch.empty(S * n * ch, dtype=torch.int16, device="cuda")
+    eng.gen_pcm_dev(pcm.data_ptr(), S, 0, ch, n, 0, 3, "music", stream)
+    p_off = np.arange(S, dtype=np.uint64) * np.uint64(n * ch)
+    o_off = np.arange(S, dtype=np.uint64) * np.uint64(frames * fbytes)
+    results = []
+    for cuts in ([32], [16, 16], [5, 27]):
+        out = torch.zeros(S * frames * fbytes, dtype=torch.uint8, device="cuda")
+        batch = eng.encoder_batch([(ch, rate, n)] * S)
+        done = 0
+        for f in cuts:
+            batch.encode_chunk_dev(pcm.data_ptr(), p_off + np.uint64(done * 5120 * ch), np.full(S, f * 5120, dtype=np.uint32),
+                                   out.data_ptr(), o_off + np.uint64(done * fbytes), stream)
+            done += f
+        torch.cuda.synchronize()
+        batch.close()
+        results.append(out)
+    assert torch.equal(results[0], results[1]) and torch.equal(results[0], results[2])
+    host = pcm.view(S, n * ch)
+    for s in sorted(set([0, 1777 % S, S - 1])):
+        ref = ob.encode_all(host[s].cpu().numpy(), ch, rate, n)[1]
+        assert results[0][s * frames * fbytes:(s + 1) * frames * fbytes].cpu().numpy().tobytes() == bytes(ref)[8:], s
