@@ -4,6 +4,7 @@
 # (tools/collect_profiles.sh).
 set -x
 O=gpurun_out
+make -s -C tools
 python bench.py > $O/final_bench_n1.json 2> $O/final_bench_n1.err
 python bench.py --impl reference > $O/final_bench_ref.json 2> $O/final_bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/final_launches.csv \
