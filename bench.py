@@ -640,15 +640,17 @@ def peak_hbm():
 
 
 def mixed_batch_leg(eng, qoa, pcm, stream):
-    """BASELINE.json configs[4]: a shuffled batch of mono / stereo / 5.1 streams of 1-60 s (partial last frames and
-    slices) decoded in one plan: every stream runs on its own class's kernel.  Reuses the resident arenas."""
+    """BASELINE.json configs[4]: a shuffled batch of mono ... 8-channel streams of 1-60 s at 8-96 kHz with odd lengths
+    (partial last frames and slices) decoded in one plan: every stream runs on its own class's kernel.  Reuses the
+    resident arenas."""
     import numpy as np
     import torch
     import qoaudio_b200 as q
     from oracle import binding as ob
     n_streams = 2048
     rng = np.random.default_rng(5)
-    chs = rng.choice([1, 2, 6], size=n_streams, p=[0.3, 0.5, 0.2])
+    chs = rng.choice([1, 2, 3, 4, 5, 6, 7, 8], size=n_streams, p=[0.2, 0.3, 0.05, 0.1, 0.05, 0.15, 0.05, 0.1])
+    rates = rng.choice([8000, 11025, 16000, 22050, 32000, 44100, 48000, 96000], size=n_streams)
     ns = rng.integers(1, 61, size=n_streams) * 44100 + rng.integers(0, 5120, size=n_streams)
     sizes = np.array([enc_size(int(c), int(n)) for n, c in zip(ns, chs)], dtype=np.uint64)
     strides = (sizes + np.uint64(15)) // np.uint64(16) * np.uint64(16)
@@ -659,7 +661,7 @@ def mixed_batch_leg(eng, qoa, pcm, stream):
     if int(strides.sum()) > qoa.numel() or int(slots.sum()) > pcm.numel():
         return None  # a reduced --streams run: the resident arenas are too small for this leg
     for i in range(n_streams):
-        eng.gen_qoa_dev(qoa.data_ptr() + int(in_off[i]), int(strides[i]), 1, i, int(chs[i]), 44100, int(ns[i]), 3, stream)
+        eng.gen_qoa_dev(qoa.data_ptr() + int(in_off[i]), int(strides[i]), 1, i, int(chs[i]), int(rates[i]), int(ns[i]), 3, stream)
     torch.cuda.synchronize()
     best = 1e9
     for it in range(4):
@@ -673,16 +675,16 @@ def mixed_batch_leg(eng, qoa, pcm, stream):
         assert (st == 0).all()
         if it:
             best = min(best, e0.elapsed_time(e1))
-    for i in (0, int(np.argmax(chs == 1)), int(np.argmax(chs == 6)), n_streams - 1):  # one stream per class + the last one
+    for i in sorted(set([int(np.argmax(chs == c)) for c in range(1, 9)] + [0, n_streams - 1])):  # one stream per class + first, last
         blob = qoa[int(in_off[i]):int(in_off[i]) + int(sizes[i])].cpu().numpy().tobytes()
         got = pcm[int(out_off[i]):int(out_off[i]) + int(caps[i])].cpu().numpy()
         assert np.array_equal(got, ob.decode_all(blob)[1]), f"mixed-batch stream {i} differs from the oracle"
     samples = int(caps.sum())
-    return {"workload": f"{n_streams} shuffled mono / stereo / 5.1 streams of 1-60 s at 44.1 kHz with partial last frames "
-                        "and slices (BASELINE.json configs[4] shape), index + decode in one plan",
+    return {"workload": f"{n_streams} shuffled 1..8-channel streams of 1-60 s (+ odd remainders) at 8-96 kHz with partial last "
+                        "frames and slices (BASELINE.json configs[4] shape), index + decode in one plan, one launch per class",
             "value": samples / best / 1e3, "unit": "Msamples/s", "ms": best, "gsamples": samples / 1e9,
-            "streams": {"mono": int((chs == 1).sum()), "stereo": int((chs == 2).sum()), "5.1": int((chs == 6).sum())},
-            "parity": "one stream per class + the last stream bit-exact vs oracle"}
+            "streams_per_channel_count": {str(c): int((chs == c).sum()) for c in range(1, 9)},
+            "parity": "one stream per channel count + first and last stream bit-exact vs oracle"}
 
 
 if __name__ == "__main__":

@@ -69,6 +69,21 @@ struct qoa_b200_ctx {
         for (auto &b : pool) b.slot = 0;
     }
     cudaStream_t pipe_streams[3] = {nullptr, nullptr, nullptr};
+    // a mixed batch launches one decode kernel per channel-count class: classes after the first run on these side
+    // streams (forked from / joined to the caller's stream by events) so that small classes overlap instead of each
+    // draining the machine on its own
+    cudaStream_t cls_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t cls_fork = nullptr, cls_join[3] = {nullptr, nullptr, nullptr};
+    bool cls_ready()
+    {
+        if (cls_fork) return true;
+        for (auto &cs : cls_streams)
+            if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) return cudaGetLastError(), false;
+        for (auto &e : cls_join)
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError(), false;
+        if (cudaEventCreateWithFlags(&cls_fork, cudaEventDisableTiming) != cudaSuccess) return cudaGetLastError(), false;
+        return true;
+    }
     // host-mapped (pinned) result slots the index kernels write directly: one region per pipeline stream
     struct Mapped {
         void *ptr = nullptr;
@@ -350,6 +365,11 @@ void qoa_b200_ctx_destroy(qoa_b200_ctx *ctx)
         if (b.ptr) cudaFree(b.ptr);
     for (auto &ps : ctx->pipe_streams)
         if (ps) cudaStreamDestroy(ps);
+    for (auto &cs : ctx->cls_streams)
+        if (cs) cudaStreamDestroy(cs);
+    for (auto &e : ctx->cls_join)
+        if (e) cudaEventDestroy(e);
+    if (ctx->cls_fork) cudaEventDestroy(ctx->cls_fork);
     for (auto &m : ctx->mapped)
         if (m.ptr) cudaFreeHost(m.ptr);
     delete ctx;
@@ -1175,14 +1195,34 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
         return QOA_B200_E_NOMEM;
     }
     CHECK_CUDA(ctx, cudaMemcpyAsync(d_base, base.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    int n_cls = 0;
+    for (int c = 0; c < 9; ++c) n_cls += plan->cls_frames[c] != 0;
+    // several classes: fork the launches over side streams (not inside a pipelined host call, whose stages already overlap)
+    const bool fork = n_cls > 1 && !ctx->pipelining && ctx->cls_ready();
+    if (fork) CHECK_CUDA(ctx, cudaEventRecord(ctx->cls_fork, s));
+    int k = 0;
+    bool used[3] = {false, false, false};
     for (int c = 0; c < 9; ++c) { // one launch per kernel class present in the batch
         if (!plan->cls_frames[c]) continue;
+        cudaStream_t ls = s;
+        if (fork && k > 0) {
+            const int side = (k - 1) % 3;
+            ls = ctx->cls_streams[side];
+            if (!used[side]) CHECK_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->cls_fork, 0));
+            used[side] = true;
+        }
+        ++k;
         int nl = 0;
         CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs + plan->cls_start[c], plan->cls_frames[c],
                                       plan->cls_max_ch[c], (c && cls_aligned[c]) ? (uint32_t)c : 0u, d_base, d_out, out_bytes,
-                                      s, &nl));
+                                      ls, &nl));
         ctx->launches += nl;
     }
+    for (int side = 0; side < 3; ++side) // join: everything the caller enqueues behind this call sees every class done
+        if (used[side]) {
+            CHECK_CUDA(ctx, cudaEventRecord(ctx->cls_join[side], ctx->cls_streams[side]));
+            CHECK_CUDA(ctx, cudaStreamWaitEvent(s, ctx->cls_join[side], 0));
+        }
     return 0;
 }
 
