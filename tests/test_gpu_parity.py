@@ -521,6 +521,42 @@ def test_decode_all_batch_pipelined(eng):
         assert np.array_equal(outs[i][:infos2[i]["samples"]], outs2[i])
 
 
+def test_pipelined_host_paths_bound_device_memory(N):
+    """The pipelined host paths hold the arenas of about three pipeline stages, not of the whole batch: a block released
+    by a stage on pipeline stream k is handed out again to later stages of the same stream.  A fresh context decodes
+    1.9 GB of PCM (360 x 2.6 M samples) and then encodes it again; the device memory its pool keeps afterwards (= the
+    most it ever held) stays far below the batch."""
+    import torch
+    import qoaudio_b200 as q
+    e2 = q.Engine(0)
+    ch, rate, n = 2, 44100, 5120 * 256
+    size = ob.encoded_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    count = 360
+    t = torch.zeros(count * stride, dtype=torch.uint8, device="cuda")
+    e2.gen_qoa_dev(t.data_ptr(), stride, count, 0, ch, rate, n, 9)
+    torch.cuda.synchronize()
+    host = t.cpu().numpy()
+    del t
+    torch.cuda.empty_cache()
+    streams = [host[i * stride:i * stride + size] for i in range(count)]
+    out = np.empty((count, n * ch), dtype=np.int16)
+    free0, _ = torch.cuda.mem_get_info()
+    info, status, views = e2.decode_all_batch(streams, [n * ch] * count, out=out)
+    free1, _ = torch.cuda.mem_get_info()
+    assert not status.any()
+    batch_bytes = count * (size + n * ch * 2)
+    assert batch_bytes > 2.2e9 and free0 - free1 < 0.45 * batch_bytes, (free0 - free1, batch_bytes)
+    for i in (0, 179, 359):
+        assert np.array_equal(out[i], ob.decode_all(streams[i].tobytes())[1]), i
+    st, enc = e2.encode_all_batch(list(out), [(ch, rate, n)] * count)        # 1.9 GB of PCM: time-chunked pipeline
+    free2, _ = torch.cuda.mem_get_info()
+    assert st == [0] * count and free0 - free2 < 0.6 * batch_bytes, (free0 - free2, batch_bytes)
+    for i in (0, 359):
+        assert enc[i].tobytes() == ob.encode_all(out[i], ch, rate, n)[1], i
+    e2.close()
+
+
 def test_batch_tensor_rows_move_as_strided_copies(eng):
     """Equal-length streams held as rows of one array (input and output) travel as single strided copies
     (cudaMemcpy2DAsync) instead of one copy per stream; results must not depend on how the bytes travelled."""
