@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8192, help="decode streams per GPU (weak scaling) = total streams of the strong-scaling run")
     ap.add_argument("--enc-streams", type=int, default=4096, help="encode streams per GPU (weak) = total streams of the strong-scaling run")
     ap.add_argument("--enc-frames", type=int, default=16, help="frames per stream per encode step (time chunk)")
-    ap.add_argument("--e2e-streams", type=int, default=128)
+    ap.add_argument("--e2e-streams", type=int, default=256)
     ap.add_argument("--no-encode", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -604,6 +604,17 @@ def main():
         traffic_src = "static: " + t["source"]
     except Exception:  # noqa: BLE001
         pass
+    # The bound that actually binds: per stereo sample pair the loop needs 16 IMAD (FMA-heavy pipe) and 17
+    # ALU-pipe instructions; each pipe accepts one warp instruction per two cycles, so a warp needs >= 33 cycles per pair
+    # with both pipes perfectly overlapped.  tools/core_probe.cu measures the same ladder without memory traffic.
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    pairs_per_launch = S * DEC_SAMPLES
+    floor_ms = pairs_per_launch / 32 / (sm_count * 4) * 33 / ((clocks.get("sm_max_mhz") or 1965) * 1e6) * 1e3
+    int_pipes = {"bound": "int32 pipes (FMA-heavy + ALU, one warp instruction per two cycles each)",
+                 "per_sample_pair": {"imad": 16, "alu": 17, "lds": 2}, "floor_cycles_per_warp_and_pair": 33,
+                 "floor_ms_at_max_clock": floor_ms, "kernel_ms": kern_ms, "frac": floor_ms / kern_ms,
+                 "probe": "tools/core_probe.cu: pair_core alone 19.7 ms, + table lookups 23.6 ms, full kernel 26.2 ms "
+                          "at 1965 MHz (profiles/r02_core_probe.txt)"}
     line = {
         "metric": "batch decode throughput", "value": dec_value, "unit": "Msamples/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": dec_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -615,7 +626,8 @@ def main():
                      "peak_kind": "MEASURED_PEAKS.json hbm_gbs (of measured)" if PEAKS.get("hbm_gbs") else "of fallback",
                      "note": "the kernel is bound by integer issue (16 IMAD + 12 ALU per stereo sample pair on two "
                              "half-rate pipes), not by HBM: DRAM ~48 % busy, traffic = 1.02 x algorithmic "
-                             "(profiles/r02_decode_experiments.md)"},
+                             "(profiles/r02_decode_experiments.md)",
+                     "int_pipe_roofline": int_pipes},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
         "scaling_strong": strong, "mixed_batch": mixed,
         "encode": encode, "single_stream": single,
