@@ -51,6 +51,10 @@ for r in range(rounds):
         n = int(rng.integers(100000, 300000))
         pcm.append(signal(n))
         descs.append((1, 44100, n))
+    for ch in range(1, 9):  # long enough for whole warps of full frames: the uniform-warp / tensor-store decode paths
+        n = int(rng.integers(5120 * 40, 5120 * 70))
+        pcm.append(signal(n * ch))
+        descs.append((ch, 48000, n))
     order = rng.permutation(len(pcm))
     pcm, descs = [pcm[k] for k in order], [descs[k] for k in order]
     expect = [ob.encode_all(p, *d)[1] for p, d in zip(pcm, descs)]
