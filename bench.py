@@ -203,6 +203,10 @@ def main():
     ap.add_argument("--no-single", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip noise / seeds / full-length / mixed-batch / strong-scaling legs")
     args = ap.parse_args()
+    # A bench that hangs (a lost device, a rank that died before a barrier) must not hold the box until the driver's own
+    # limit: after QOA_B200_BENCH_WATCHDOG_S seconds (default 40 min, far above any run) dump the stacks and exit.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("QOA_B200_BENCH_WATCHDOG_S", "2400")), exit=True)
     if args.impl == "reference":
         return run_reference(args)
 

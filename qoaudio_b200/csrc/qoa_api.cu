@@ -8,6 +8,7 @@
 // There is deliberately no CPU implementation of encode/decode in this file: without a CUDA device every compute
 // entry point fails with QOA_B200_E_CUDA.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -237,7 +238,7 @@ int copy_batch(qoa_b200_ctx *ctx, Scratch &sc, const std::vector<CopyItem> &item
     //      cudaMemcpyAsync per buffer (4-8 us of host time each).
     static const bool kernel_on = !(getenv("QOA_B200_COPY_KERNEL") && atoi(getenv("QOA_B200_COPY_KERNEL")) == 0);
     static const bool use_2d = !(getenv("QOA_B200_COPY_2D") && atoi(getenv("QOA_B200_COPY_2D")) == 0);
-    static bool use_batch = !(getenv("QOA_B200_COPY_BATCH") && atoi(getenv("QOA_B200_COPY_BATCH")) == 0);
+    static std::atomic<bool> use_batch{!(getenv("QOA_B200_COPY_BATCH") && atoi(getenv("QOA_B200_COPY_BATCH")) == 0)}; // written by any host thread
     static const long env_h2d = getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D") ? atol(getenv("QOA_B200_COPY_KERNEL_MAX_KB_H2D")) : -1;
     static const long env_d2h = getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H") ? atol(getenv("QOA_B200_COPY_KERNEL_MAX_KB_D2H")) : -1;
 #if CUDART_VERSION >= 12080
@@ -1109,6 +1110,7 @@ static int plan_create_host(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const 
 extern "C" int qoa_b200_decode_plan_create(qoa_b200_ctx *ctx, const uint8_t *const *qoa, const size_t *len, size_t n,
                                            int mode, qoa_b200_decode_plan **out)
 {
+    if (!ctx || !out) return QOA_B200_E_ARG;
     if (cudaSetDevice(ctx->device) != cudaSuccess) cudaGetLastError(); // reported by plan_create_host
     return plan_create_host(ctx, qoa, len, n, mode, ctx->host_stream(), out);
 }
@@ -1202,27 +1204,33 @@ extern "C" int qoa_b200_decode_plan_run_dev(qoa_b200_decode_plan *plan, int16_t 
     if (fork) CHECK_CUDA(ctx, cudaEventRecord(ctx->cls_fork, s));
     int k = 0;
     bool used[3] = {false, false, false};
-    for (int c = 0; c < 9; ++c) { // one launch per kernel class present in the batch
+    cudaError_t e = cudaSuccess; // no early return between fork and join: a side stream is never left unjoined
+    for (int c = 0; c < 9 && e == cudaSuccess; ++c) { // one launch per kernel class present in the batch
         if (!plan->cls_frames[c]) continue;
         cudaStream_t ls = s;
         if (fork && k > 0) {
             const int side = (k - 1) % 3;
+            if (!used[side] && (e = cudaStreamWaitEvent(ctx->cls_streams[side], ctx->cls_fork, 0)) != cudaSuccess) break;
             ls = ctx->cls_streams[side];
-            if (!used[side]) CHECK_CUDA(ctx, cudaStreamWaitEvent(ls, ctx->cls_fork, 0));
             used[side] = true;
         }
         ++k;
         int nl = 0;
-        CHECK_CUDA(ctx, launch_decode(plan->d_arena, plan->d_recs + plan->cls_start[c], plan->cls_frames[c],
-                                      plan->cls_max_ch[c], (c && cls_aligned[c]) ? (uint32_t)c : 0u, d_base, d_out, out_bytes,
-                                      ls, &nl));
+        e = launch_decode(plan->d_arena, plan->d_recs + plan->cls_start[c], plan->cls_frames[c], plan->cls_max_ch[c],
+                          (c && cls_aligned[c]) ? (uint32_t)c : 0u, d_base, d_out, out_bytes, ls, &nl);
         ctx->launches += nl;
     }
     for (int side = 0; side < 3; ++side) // join: everything the caller enqueues behind this call sees every class done
         if (used[side]) {
-            CHECK_CUDA(ctx, cudaEventRecord(ctx->cls_join[side], ctx->cls_streams[side]));
-            CHECK_CUDA(ctx, cudaStreamWaitEvent(s, ctx->cls_join[side], 0));
+            cudaError_t ej = cudaEventRecord(ctx->cls_join[side], ctx->cls_streams[side]);
+            if (ej == cudaSuccess) ej = cudaStreamWaitEvent(s, ctx->cls_join[side], 0);
+            if (e == cudaSuccess) e = ej;
         }
+    if (e != cudaSuccess) {
+        ctx->err = std::string("decode launch: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return QOA_B200_E_CUDA;
+    }
     return 0;
 }
 

@@ -10,8 +10,22 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+GPU_TEST_TIMEOUT_S = 900  # the slowest GPU test (full-size configs[2] properties) takes about a minute on a B200
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs (a kernel that never ends, a lost device) must end the run instead of holding the box:
+    every `gpu` test without its own limit gets one.  method="thread": a blocked CUDA call never returns to the
+    interpreter, so a signal handler would never run; the watchdog thread dumps the stacks and exits the process."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(GPU_TEST_TIMEOUT_S, method="thread"))
 
 
 @pytest.fixture(scope="session", autouse=True)
