@@ -7,12 +7,18 @@
  *
  * Parity pin status:
  *   - decode: pinned by the reference's own fixture tests (src/lib.rs:998-1074): mode,
- *     468 frame headers, per-frame sample counts, 2394122*2 samples.  No sample VALUES are
- *     asserted anywhere in the reference.
+ *     468 frame headers, per-frame sample counts, 2394122*2 samples.  The reference's tests
+ *     assert no sample VALUES, but its fixture holds them: the file was written by another
+ *     encoder, which stored its LMS state in every frame header, and the state this decoder
+ *     reaches at the end of each frame equals the next header's, 934 times x 128 bits
+ *     (oracle/vector_verify.py, tests/test_vector_verify.py) - a reference-held check of the
+ *     decode arithmetic over every sample of every full frame.
  *   - encode: PARITY UNPINNED by golden vectors.  The reference holds no byte-level encoder
  *     golden; the Rust crate cannot be built here (no rustc/cargo).  The pin is this
  *     restatement + an independent brute-force search (encode_slice_brute) + an independent
- *     pure-Python restatement (oracle/qoa_pyref.py) + SURVEY.md Appendix B hashes.
+ *     pure-Python restatement (oracle/qoa_pyref.py) + a slice-parallel torch verifier
+ *     (oracle/vector_verify.py: all 16 candidates of every slice, lexicographic arg-min)
+ *     + SURVEY.md Appendix B hashes.
  *
  * Every function cites the reference file:line it follows (paths relative to the reference
  * repo root, i.e. src/lib.rs).

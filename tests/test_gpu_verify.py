@@ -55,7 +55,7 @@ def test_full_size_decode_every_sample_of_every_fourth_stream(eng, N):
     import torch
     torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
-    S = 8192 if free > 150e9 else (1024 if free > 24e9 else 128)
+    S = 8192 if free > 150e9 else 1024 if free > 24e9 else 128 if free > 4e9 else 12
     ch, rate, n = 2, 44100, 2646000
     size = enc_size(ch, n)
     stride = (size + 15) // 16 * 16
@@ -88,7 +88,7 @@ def test_full_width_encode_every_slice(eng, N, kind, streams):
     import torch
     torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
-    S = streams if free > 40e9 else min(streams, 256)
+    S = streams if free > 40e9 else min(streams, 256) if free > 4e9 else 24
     ch, rate, n = 2, 48000, 5120 * 8 + 333
     size = enc_size(ch, n)
     stride = (size + 15) // 16 * 16
