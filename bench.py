@@ -230,6 +230,23 @@ def main():
     extras = not args.no_extras
     Ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
+    def guarded(name, fn, collective=False):
+        """The optional legs must not cost the headline line: a failure inside one is reported in that leg's object
+        ({"error": ...}, loud in the JSON) instead of ending the run.  Legs with barriers in them are only guarded in a
+        single-process run (a rank that skipped a barrier would leave the others waiting)."""
+        if collective and world > 1:
+            return fn()
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            sys.stderr.write(f"bench leg {name} failed:\n{traceback.format_exc()}\n")
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
+
     # ---------------------------------------------------------------- decode (headline) -------------------------
     S = args.streams
     size = enc_size(DEC_CH, DEC_SAMPLES)
@@ -309,7 +326,8 @@ def main():
 
     # ---------------------------------------------------------------- e2e: host buffers through the C ABI -------
     e2e = None
-    if not args.no_e2e:
+
+    def e2e_leg():
         E = min(args.e2e_streams, S)
         h_in = qoa[:E * stride].cpu().pin_memory()
         h_out = torch.empty(E * out_per, dtype=torch.int16).pin_memory()
@@ -367,11 +385,15 @@ def main():
                     "host_ceiling_note": "same H2D + D2H bytes per step as bare pinned cudaMemcpyAsync on two streams per "
                                          "rank, all ranks concurrently: aggregate host<->device GB/s of this box"})
         del h_in, h_out, d_in
+        return e2e
+
+    if not args.no_e2e:
+        e2e = guarded("e2e", e2e_leg, collective=True)
 
     # ---------------------------------------------------------------- configs[4]: a shuffled mixed batch ---------
     mixed = None
     if rank == 0 and extras:
-        mixed = mixed_batch_leg(eng, qoa, pcm, stream)
+        mixed = guarded("mixed_batch", lambda: mixed_batch_leg(eng, qoa, pcm, stream))
     del pcm, qoa
     torch.cuda.empty_cache()
 
@@ -471,7 +493,7 @@ def main():
                                "measured_issue_peaks_tops": {k: v / 1e12 for k, v in measured.items()},
                                "frac_of_measured_mix_peak": per_gpu_ops / measured["mix"], "traffic": None},
                   "clocks": main_run["clocks"], "parity": enc_parity}
-        if extras:
+        def encode_extras():
             # white noise (worst case for the CPU's pruning; identical work for the GPU's lock-step search) and seeds 2, 3
             variants = {}
             for kind, seed in (("noise", 1), ("music", 2), ("music", 3)):
@@ -505,9 +527,16 @@ def main():
                 strong["encode"] = {"value": ES * chunk * ENC_CH * KE / (r["ms"] * 1e-3) / 1e6, "unit": "Msamples/s",
                                     "streams_total": ES, "streams_per_gpu": e - b, "ms_per_step": r["ms"] / KE,
                                     "kernel": "latency-mode encode kernel" if (e - b) <= 1184 else "throughput encode kernel"}
+            return True
+
+        if extras:
+            ok = guarded("encode_extras", encode_extras, collective=True)
+            if ok is not True:
+                encode["extras_error"] = ok["error"]
+
         # e2e: the same shape through qoa_b200_encode_all_batch with pinned HOST buffers (time-chunked pipeline:
         # H2D of chunk t+1 || kernel of chunk t || D2H of chunk t-1); 24 frames per stream per call
-        if not args.no_e2e:
+        def encode_e2e():
             import ctypes as C
             N = q._native
             EF = 24
@@ -544,12 +573,17 @@ def main():
                              "h2d_bytes_per_step": ES * per * 2, "d2h_bytes_per_step": ES * osz, "ms_per_step": dt / reps * 1e3,
                              "api": "qoa_b200_encode_all_batch (pinned host buffers, 24 frames per stream per call, pipelined in time chunks of ~176 MB of PCM)"}
             del h_pcm, h_enc
+            return encode["e2e"]
+
+        if not args.no_e2e:
+            encode["e2e"] = guarded("encode_e2e", encode_e2e, collective=True)
         del epcm, eout
 
     # ---------------------------------------------------------------- configs[1]: ONE 54 s stereo stream --------
     # Latency-bound by construction (encode = one warp, decode = 466 threads): reported, not tuned for.
     single = None
-    if rank == 0 and not args.no_single:
+
+    def single_leg():
         SN, SCH, SRATE = 2381400, 2, 44100
         spcm = torch.empty(SN * SCH, dtype=torch.int16, device=dev)
         eng.gen_pcm_dev(spcm.data_ptr(), 1, 0, SCH, SN, 0, 1, "music", stream)
@@ -588,6 +622,10 @@ def main():
             single.update({"cpu_encode_ms": (t1 - t0) * 1e3, "cpu_decode_ms": (t2 - t1) * 1e3,
                            "parity": "bit-exact vs oracle"})
         del spcm, sq, sout
+        return single
+
+    if rank == 0 and not args.no_single:
+        single = guarded("single_stream", single_leg)
 
     if rank != 0:
         grp.close()
