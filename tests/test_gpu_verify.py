@@ -114,3 +114,63 @@ def test_full_width_encode_every_slice(eng, N, kind, streams):
     assert r["streams"] == S and r["slices"] == S * ch * ((n + 19) // 20) and r["boundaries"] == S * ch * 8
     if kind == "music":
         assert r["unverifiable_slices"] == 0
+
+
+@pytest.mark.parametrize("ch", [1, 3, 4, 5, 6, 7, 8])
+def test_long_streams_every_sample_other_channel_counts(eng, N, ch):
+    """The mono fast kernel and the 3..8-channel kernels on long streams (40 full frames + a partial one with a partial
+    last slice: uniform-warp loop / tensor-store path, stream boundaries inside warps, the row-copy path for the
+    tails): every sample of every stream against the recurrences."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    S = 96 if free > 4e9 else 5
+    rate, n = 48000, 5120 * 40 + 1234
+    size = enc_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    per = (n * ch + 7) // 8 * 8                              # 16-byte aligned slots
+    stream = torch.cuda.current_stream().cuda_stream
+    qoa = torch.empty(S * stride, dtype=torch.uint8, device="cuda")
+    pcm = torch.full((S * per,), 99, dtype=torch.int16, device="cuda")
+    eng.gen_qoa_dev(qoa.data_ptr(), stride, S, 0, ch, rate, n, 20 + ch, stream)
+    offs = np.arange(S, dtype=np.uint64)
+    plan = eng.decode_plan_dev(qoa.data_ptr(), offs * np.uint64(stride), np.full(S, size, dtype=np.uint64), N.DECODE_ALL, stream)
+    st = plan.run_dev(pcm.data_ptr(), offs * np.uint64(per), np.full(S, n * ch, dtype=np.uint64), stream)
+    torch.cuda.synchronize()
+    assert (st == 0).all() and (plan.info_array["samples"] == n * ch).all()
+    plan.close()
+    r = vc.decode_in_chunks(qoa.view(S, stride), pcm.view(S, per), ch, n, rate, chunk=8)
+    assert all(r[k] == 0 for k in CLEAN_DECODE), r
+    assert r["streams"] == S and r["samples"] == S * n * ch
+    assert (pcm.view(S, per)[:, n * ch:] == 99).all()        # nothing written behind a stream
+
+
+@pytest.mark.parametrize("ch,kind", [(1, "music"), (3, "noise"), (8, "music")])
+def test_encode_every_slice_other_channel_counts(eng, N, ch, kind):
+    """Mono, 3- and 8-channel encodes (chains = streams x channels, interleaved input): every slice is the arg-min
+    candidate, every header chains."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    S = 192 if free > 4e9 else 6
+    rate, n = 44100, 5120 * 3 + 4097
+    size = enc_size(ch, n)
+    stride = (size + 15) // 16 * 16
+    per = n * ch
+    stream = torch.cuda.current_stream().cuda_stream
+    src = torch.empty(S * per, dtype=torch.int16, device="cuda")
+    eng.gen_pcm_dev(src.data_ptr(), S, 0, ch, n, 0, 6, kind, stream)
+    qoa = torch.zeros(S * stride, dtype=torch.uint8, device="cuda")
+    offs = np.arange(S, dtype=np.uint64)
+    st, out_len = eng.encode_all_batch_dev([(ch, rate, n)] * S, src.data_ptr(), offs * np.uint64(per),
+                                           np.full(S, per, dtype=np.uint64), qoa.data_ptr(), offs * np.uint64(stride),
+                                           np.full(S, size, dtype=np.uint64), stream)
+    assert st == [0] * S and out_len == [size] * S
+    dper = (per + 7) // 8 * 8
+    dec = torch.full((S * dper,), -5, dtype=torch.int16, device="cuda")
+    plan = eng.decode_plan_dev(qoa.data_ptr(), offs * np.uint64(stride), np.full(S, size, dtype=np.uint64), N.DECODE_ALL, stream)
+    dst = plan.run_dev(dec.data_ptr(), offs * np.uint64(dper), np.full(S, per, dtype=np.uint64), stream)
+    torch.cuda.synchronize()
+    assert (dst == 0).all() and (plan.info_array["samples"] == per).all()
+    plan.close()
+    r = vc.encode_in_chunks(qoa.view(S, stride), src.view(S, per), dec.view(S, dper), ch, n, rate, chunk=64, max_lanes=1 << 24)
+    assert all(r[k] == 0 for k in CLEAN_ENCODE), r
+    assert r["streams"] == S and r["slices"] == S * ch * ((n + 19) // 20)

@@ -85,3 +85,7 @@ def test_gpu_verify_bodies_on_a_stand_in_engine(fixture_bytes, monkeypatch):
     mod.test_full_size_decode_every_sample_of_every_fourth_stream(eng, native)
     mod.test_full_width_encode_every_slice(eng, native, "music", 4096)
     mod.test_full_width_encode_every_slice(eng, native, "noise", 512)
+    for ch in (1, 3, 6, 7):
+        mod.test_long_streams_every_sample_other_channel_counts(eng, native, ch)
+    for ch, kind in ((1, "music"), (3, "noise"), (8, "music")):
+        mod.test_encode_every_slice_other_channel_counts(eng, native, ch, kind)
