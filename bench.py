@@ -309,6 +309,18 @@ def main():
             _, ref = ob.decode_all(blob)
             assert np.array_equal(got, ref), f"bench decode of stream {s} differs from the oracle"
         parity = "streams 0 and last bit-exact vs oracle"
+        if extras:
+            # ... and EVERY sample of 64 streams spread over the batch against the decode recurrences, on the device, with
+            # the vectorised verifier (oracle/vector_verify.py: checker only, torch kernels, untimed)
+            def verify_leg():
+                import verify_chunks as vc
+                pick = sorted(set(int(v) for v in np.linspace(0, S - 1, min(S, 64))))
+                r = vc.decode_in_chunks(qoa.view(S, stride), pcm.view(S, out_slot), DEC_CH, DEC_SAMPLES, DEC_RATE,
+                                        streams=pick, chunk=8)
+                assert r["bad_samples"] == 0 and r["bad_frame_headers"] == 0 and r["bad_file_headers"] == 0, r
+                return f"; all {r['samples']} samples of {r['streams']} streams satisfy the decode recurrences (verified on the device)"
+            v = guarded("decode_verify", verify_leg)
+            parity += v if isinstance(v, str) else f"; device-side verifier leg failed: {v['error']}"
     # strong scaling: the SAME 8192-stream batch split over the ranks (BASELINE.json configs[2] "at 1/2/4/8 B200")
     strong = {"decode": None, "encode": None, "note": "total batch fixed (configs[2]/[3] as written), streams split by "
               "qoa_b200_partition over the ranks; the headline `value` is the weak-scaling number (batch per GPU fixed)"}
