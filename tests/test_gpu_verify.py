@@ -28,6 +28,18 @@ def N():
     return n
 
 
+def assert_clean_encode(r, kind):
+    """Every sample, slice and initial state must verify.  The frame-to-frame chain is exact unless a weight left the
+    16-bit range at a frame boundary (src/lib.rs:459-460 truncates what :482 carries in full; never seen on these
+    signals, 4096 noise boundaries checked on the CPU): behind such a boundary encoder and decoder legitimately differ,
+    the slices there are counted as unverifiable and the chain counters are not asserted."""
+    assert all(r[k] == 0 for k in CLEAN_DECODE + ("bad_slices", "bad_initial_state")), r
+    if r["truncated_boundaries"] == 0:
+        assert all(r[k] == 0 for k in CLEAN_CHAIN) and r["unverifiable_slices"] == 0, r
+    if kind == "music":
+        assert r["truncated_boundaries"] == 0, r
+
+
 def enc_size(ch, n):
     return 8 + ((n + 5119) // 5120) * (8 + 16 * ch) + ((n + 19) // 20) * 8 * ch
 
@@ -110,10 +122,8 @@ def test_full_width_encode_every_slice(eng, N, kind, streams):
     plan.close()
     r = vc.encode_in_chunks(qoa.view(S, stride), src.view(S, per), dec.view(S, per), ch, n, rate, chunk=128,
                             max_lanes=1 << 25)
-    assert all(r[k] == 0 for k in CLEAN_ENCODE), r
+    assert_clean_encode(r, kind)
     assert r["streams"] == S and r["slices"] == S * ch * ((n + 19) // 20) and r["boundaries"] == S * ch * 8
-    if kind == "music":
-        assert r["unverifiable_slices"] == 0
 
 
 @pytest.mark.parametrize("ch", [1, 3, 4, 5, 6, 7, 8])
@@ -172,5 +182,5 @@ def test_encode_every_slice_other_channel_counts(eng, N, ch, kind):
     assert (dst == 0).all() and (plan.info_array["samples"] == per).all()
     plan.close()
     r = vc.encode_in_chunks(qoa.view(S, stride), src.view(S, per), dec.view(S, dper), ch, n, rate, chunk=64, max_lanes=1 << 24)
-    assert all(r[k] == 0 for k in CLEAN_ENCODE), r
+    assert_clean_encode(r, kind)
     assert r["streams"] == S and r["slices"] == S * ch * ((n + 19) // 20)
