@@ -179,3 +179,20 @@ def test_chunked_drivers_on_cpu():
     qoa[:, :len(enc[0])] = u8(enc)
     r = vc.encode_in_chunks(qoa, i16(src), i16(dec), ch, n, 48000, chunk=4, max_lanes=1 << 16)
     assert all(r[k] == 0 for k in CLEAN_ENCODE) and r["streams"] == S and r["slices"] == S * ch * (-(-n // 20)), r
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_random_payload_decode_all_channel_counts(ch):
+    """Random slice words and random 16-bit LMS states (weights far outside what an encoder produces: the i32 wrap of
+    predict, src/lib.rs:799-805, is exercised) for 1..8 channels, with a partial last frame and slice: the oracle's
+    decode is the fixed point of the recurrences; one flipped sample is found."""
+    rng = np.random.default_rng(100 + ch)
+    n, S = 5120 * 2 + 20 * 37 + 11, 4
+    files = [random_payload_stream(rng, ch, 32000, n) for _ in range(S)]
+    pcms = [ob.decode_all(f)[1] for f in files]
+    assert all(p.size == n * ch for p in pcms)
+    r = vv.verify_decode(u8(files), i16(pcms), ch, n, 32000)
+    assert r["bad_samples"] == 0 and r["bad_frame_headers"] == 0 and r["bad_file_headers"] == 0 and r["samples"] == S * n * ch
+    pcms[2][n * ch - 1] ^= 0x40                              # the very last sample (inside the partial slice)
+    r = vv.verify_decode(u8(files), i16(pcms), ch, n, 32000)
+    assert r["bad_samples"] == 1 and r["bad_streams"] == 1
